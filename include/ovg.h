@@ -1,0 +1,119 @@
+/* libovg -- C ABI of the B200-native OmniVGGT hot path (sm_100a).
+ *
+ * The reference has no FFI / plugin layer: its boundary is the Python nn.Module API of
+ * omnivggt/models/omnivggt.py:10-68.  The drop-in module `omnivggt-official_b200.OmniVGGT` keeps that API and
+ * binds the entry points below through ctypes.  Every entry point
+ *   - takes plain device pointers / sizes (no torch types) and a CUDA stream handle (cudaStream_t as void*),
+ *   - enqueues work asynchronously on that stream and returns 0, or a negative OVG_E_* code after recording a
+ *     message retrievable with ovg_last_error(),
+ *   - never allocates device memory on the hot path and never falls back to the CPU.
+ * Each declaration cites the reference code (file:line under /root/reference) whose arithmetic it replaces.
+ */
+#ifndef OVG_H_
+#define OVG_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OVG_OK 0
+#define OVG_E_INVALID (-1) /* bad argument (shape / alignment / null pointer) */
+#define OVG_E_CUDA (-2)    /* CUDA runtime or driver error; see ovg_last_error() */
+#define OVG_E_NODEVICE (-3)
+
+/* Library / device ------------------------------------------------------------------------------------- */
+int ovg_version(void);               /* ABI version, currently 1 */
+const char* ovg_last_error(void);    /* thread-local message of the last failing call */
+int ovg_device_check(void);          /* OVG_OK iff the current device is sm_100 (B200); OVG_E_NODEVICE otherwise */
+long long ovg_launch_count(void);    /* kernels launched by this library since load (bench.py "gpu_launches") */
+
+/* Fused tcgen05 GEMM ------------------------------------------------------------------------------------
+ *   acc[m, n] = sum_{t < num_taps} sum_{c < a_cols} A[m + tap_off[t], c] * B[n, t * a_cols + c]
+ * A: bf16 [a_rows, a_cols] row stride lda; B: bf16 [n, num_taps * a_cols] row stride ldb (nn.Linear / flattened
+ * conv weight layout).  Rows of A outside [0, a_rows) read as zero, which makes a 3x3 conv over a zero-bordered
+ * NHWC map nine row-shifted GEMMs.  Epilogues (epi):
+ *   OVG_EPI_BF16     out bf16 = act(acc + bias + table[m % table_rows] + skip1 + skip2), row maps below
+ *                    (nn.Linear+GELU layers/mlp.py:35-36; DPT convs heads/dpt_head.py:69-126,:379-399)
+ *   OVG_EPI_RESID    out fp32 [row, n] += gamma[n] * (acc + bias[n]); row = row_index ? row_index[m] : m
+ *                    (proj/fc2 + LayerScale + residual: layers/block.py:82-86,:105-106, layers/layer_scale.py:26-27;
+ *                     depth-token scatter-add: omnivggt_aggregator.py:199-212)
+ *   OVG_EPI_QKV      bias, q/k LayerNorm(64), 2-D RoPE, q pre-scale, head-major bf16 q/k/v
+ *                    (layers/attention.py:52-58, layers/rope.py:154-188)
+ *   OVG_EPI_HEADTAIL ReLU, 1x1 conv 32->outc, depth/point/confidence activations, fp32 NHWC outputs
+ *                    (heads/dpt_head.py:121-126,:255-260, heads/head_act.py:61-125)
+ */
+enum { OVG_EPI_BF16 = 0, OVG_EPI_RESID = 1, OVG_EPI_QKV = 2, OVG_EPI_HEADTAIL = 3 };
+enum {
+  OVG_ROWS_IDENT = 0,     /* out row = m */
+  OVG_ROWS_DENSE2PAD = 1, /* m = (f, y, x) on a gh x gw grid -> zero-bordered (gh+2) x (gw+2) grid */
+  OVG_ROWS_PAD = 2,       /* m already enumerates the zero-bordered grid; border rows are written as zeros */
+  OVG_ROWS_PIXSHUF = 3    /* transposed conv k = s = ps: n = (ky*ps + kx)*cout + co -> pixel (y*ps+ky, x*ps+kx) */
+};
+enum { OVG_ACT_NONE = 0, OVG_ACT_GELU_ERF = 1, OVG_ACT_RELU = 2 };
+
+typedef struct ovg_gemm_args {
+  const void* a; long long a_rows; int a_cols; long long lda;
+  const void* b; int n; long long ldb;
+  int m;
+  int num_taps; int tap_off[9];
+  int epi;
+  /* common */
+  const float* bias; int act; void* out; long long ldo;
+  /* OVG_EPI_BF16 */
+  const float* table; int table_rows;
+  const void* skip1; const void* skip2;
+  int rowmap; int gh; int gw; int ps; int cout;
+  /* OVG_EPI_RESID */
+  const float* gamma; const int* row_index;
+  /* OVG_EPI_QKV */
+  void* q_out; void* k_out; void* v_out;
+  int C; int ntok; int T; int nspecial; int wp; int maxpos;
+  const float* qn_w; const float* qn_b; const float* kn_w; const float* kn_b;
+  const float* rope_cos; const float* rope_sin; float qscale;
+  /* OVG_EPI_HEADTAIL */
+  const float* w2; const float* b2; int outc; int head_act; float* preds; float* conf;
+  /* tuning: 0 = auto, else 32/64/128/256 */
+  int block_n;
+} ovg_gemm_args;
+
+int ovg_gemm(const ovg_gemm_args* args, void* stream);
+
+/* Fused attention: out[b, i, h*64:(h+1)*64] = softmax_j(q[b,h,i,:] . k[b,h,j,:]) v[b,h,j,:], q pre-scaled by
+ * log2(e)/sqrt(64).  q,k,v: bf16 [batch, heads, n, 64]; out: bf16 [batch, n, heads*64].
+ * Replaces F.scaled_dot_product_attention, layers/attention.py:61-66. */
+int ovg_attention(const void* q, const void* k, const void* v, void* out, int batch, int heads, int n, void* stream);
+
+/* LayerNorm over the last dim, fp32 or bf16 in -> bf16 out, optional affine, optional row gather
+ * (out row m <- in row (m / grp_out) * grp_in + grp_off + m % grp_out; grp_out = 0: identity).
+ * layers/block.py:50,:67 (eps 1e-5); heads/dpt_head.py:66,:219-227. */
+int ovg_layernorm(const void* in, int in_is_bf16, long long ld_in, void* out, long long ld_out, int rows, int C,
+                  const float* w, const float* b, float eps, int grp_out, int grp_in, int grp_off, void* stream);
+
+/* Token assembly + modality scatter (omnivggt_aggregator.py:155-156,:202-213; aggregator.py:343-366). */
+int ovg_assemble_tokens(float* x, const float* patch, const float* cam_tok, const float* reg_tok, const float* inj0,
+                        const float* placeholder, const int* has_depth, int K, int S, int T, int R, int C,
+                        void* stream);
+
+/* Per-layer camera-token injection + bf16 snapshot of the residual stream into one half of the [K*T, 2C]
+ * DPT input slot + fp32 camera-token copy (omnivggt_aggregator.py:273-303,:248-251; camera_head.py:96-99). */
+int ovg_inject_snapshot(float* x, const float* inj, void* slot, float* cam_out, int K, int T, int C, int coff,
+                        void* stream);
+
+/* Depth modality: masked per-scene mean over the selected views, then [depth/(mean+1e-8)*mask, mask] im2col rows
+ * (2*patch*patch wide, row stride ldc) for the patch-embedding GEMM (omnivggt_aggregator.py:107-128,:189-199;
+ * layers/patch_embed.py:65-77).  scratch: B * 128 * 2 doubles. */
+int ovg_depth_im2col(const float* depth, const float* mask, const int* idx, double* scratch, void* cols, int ldc,
+                     int B, int S, int Sd, int H, int W, int patch, void* stream);
+
+/* im2col for the stride-2 3x3 conv (heads/dpt_head.py:93-95): bf16 NHWC [F,h,w,C] -> [F*oh*ow, 9*C]. */
+int ovg_im2col3x3s2(const void* src, void* dst, int F, int h, int w, int C, void* stream);
+
+/* Bilinear align_corners=True upsampling between zero-bordered bf16 NHWC maps, optional fp32 additive table
+ * [H*W, C] (heads/dpt_head.py:242-250,:466,:472-497). */
+int ovg_upsample_bilinear(const void* src, void* dst, const float* table, int F, int h, int w, int H, int W, int C,
+                          void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OVG_H_ */

@@ -1,0 +1,105 @@
+"""ctypes binding of libovg.so (include/ovg.h).  There is NO fallback: if the shared library is missing or the
+device is not a B200 the import / first call fails loudly."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libovg.so")
+
+EPI_BF16, EPI_RESID, EPI_QKV, EPI_HEADTAIL = 0, 1, 2, 3
+ROWS_IDENT, ROWS_DENSE2PAD, ROWS_PAD, ROWS_PIXSHUF = 0, 1, 2, 3
+ACT_NONE, ACT_GELU, ACT_RELU = 0, 1, 2
+
+_vp, _i, _ll, _f = C.c_void_p, C.c_int, C.c_longlong, C.c_float
+
+
+class GemmArgs(C.Structure):
+    """Mirror of ``ovg_gemm_args`` (include/ovg.h); field order must match exactly."""
+    _fields_ = [
+        ("a", _vp), ("a_rows", _ll), ("a_cols", _i), ("lda", _ll),
+        ("b", _vp), ("n", _i), ("ldb", _ll),
+        ("m", _i),
+        ("num_taps", _i), ("tap_off", _i * 9),
+        ("epi", _i),
+        ("bias", _vp), ("act", _i), ("out", _vp), ("ldo", _ll),
+        ("table", _vp), ("table_rows", _i),
+        ("skip1", _vp), ("skip2", _vp),
+        ("rowmap", _i), ("gh", _i), ("gw", _i), ("ps", _i), ("cout", _i),
+        ("gamma", _vp), ("row_index", _vp),
+        ("q_out", _vp), ("k_out", _vp), ("v_out", _vp),
+        ("C", _i), ("ntok", _i), ("T", _i), ("nspecial", _i), ("wp", _i), ("maxpos", _i),
+        ("qn_w", _vp), ("qn_b", _vp), ("kn_w", _vp), ("kn_b", _vp),
+        ("rope_cos", _vp), ("rope_sin", _vp), ("qscale", _f),
+        ("w2", _vp), ("b2", _vp), ("outc", _i), ("head_act", _i), ("preds", _vp), ("conf", _vp),
+        ("block_n", _i),
+    ]
+
+
+EXPORTS = {
+    "ovg_version": (C.c_int, []),
+    "ovg_last_error": (C.c_char_p, []),
+    "ovg_device_check": (C.c_int, []),
+    "ovg_launch_count": (C.c_longlong, []),
+    "ovg_gemm": (C.c_int, [C.POINTER(GemmArgs), _vp]),
+    "ovg_attention": (C.c_int, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "ovg_layernorm": (C.c_int, [_vp, _i, _ll, _vp, _ll, _i, _i, _vp, _vp, _f, _i, _i, _i, _vp]),
+    "ovg_assemble_tokens": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "ovg_inject_snapshot": (C.c_int, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "ovg_depth_im2col": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "ovg_im2col3x3s2": (C.c_int, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "ovg_upsample_bilinear": (C.c_int, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+}
+
+_lib: Optional[C.CDLL] = None
+_device_ok = False
+
+
+class OvgError(RuntimeError):
+    pass
+
+
+def load() -> C.CDLL:
+    """Load libovg.so and bind every symbol declared in include/ovg.h (no GPU needed for this step)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise OvgError(f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(there is no CPU / PyTorch fallback for the hot path)")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in EXPORTS.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def lib() -> C.CDLL:
+    """Library handle for compute calls: additionally requires a B200 as the current device."""
+    global _device_ok
+    l = load()
+    if not _device_ok:
+        if not torch.cuda.is_available():
+            raise OvgError("libovg needs a CUDA device (B200); torch.cuda.is_available() is False")
+        torch.cuda.current_device()          # make sure the primary context exists
+        check(l.ovg_device_check())
+        _device_ok = True
+    return l
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise OvgError(f"libovg error {rc}: {load().ovg_last_error().decode()}")
+
+
+def ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def stream() -> int:
+    return torch.cuda.current_stream().cuda_stream

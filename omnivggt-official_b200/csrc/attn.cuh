@@ -1,0 +1,286 @@
+// Fused softmax(Q K^T) V for head_dim 64, non-causal, ragged sequence length (sm_100a, tcgen05 + TMA).
+// Replaces F.scaled_dot_product_attention at reference layers/attention.py:61-66 for both the frame-wise
+// (batch = B*S, N = 1374) and the global (batch = B, N = S*1374) attention of models/aggregator.py:312-341.
+//
+// q is pre-scaled by (1/sqrt(64))*log2(e) in the QKV GEMM epilogue, so probabilities are exp2(s - m).
+//
+// CTA = 256 query rows (two 128-row tiles, ping-pong) of one (batch, head).  Roles:
+//   warp 0        TMA producer: Q tiles once, K/V tiles through a 4-stage ring
+//   warp 1        MMA issuer:   S_t = Q_t K^T (SS, M128 N128 K64) and O_t += P_t V (TS: P read from TMEM,
+//                               V as MN-major smem operand, M128 N64 K128); issue order PV_t(j), S_t(j+1)
+//   warps 4-7     softmax for tile 0 (one query row per thread; row = TMEM lane)
+//   warps 8-11    softmax for tile 1
+// TMEM (512 cols): S0 [0,128) S1 [128,256) O0 [256,320) O1 [320,384); P_t (bf16x2) aliases S_t[0,64).
+// Online softmax with lazy rescaling: O/l are rescaled only when the running max grows by > 8 (log2 units),
+// which is exact (the stale max cancels in O/l) and keeps P <= 256.
+#pragma once
+#include "ptx.cuh"
+
+namespace ovg {
+
+struct AttnParams {
+  int n;        // sequence length (keys == queries)
+  int heads;
+  int C;        // heads * 64 (row stride of `out`)
+  __nv_bfloat16* out;  // [batch, n, C]
+};
+
+constexpr int ATT_THREADS = 384;
+constexpr int ATT_KV_STAGES = 4;
+constexpr int ATT_TILE_BYTES = 128 * 64 * 2;
+constexpr int ATT_SMEM_BYTES = 1024 + (2 + 2 * ATT_KV_STAGES) * ATT_TILE_BYTES + 512;
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__global__ void __launch_bounds__(ATT_THREADS, 1)
+attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+            const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+  constexpr int NS = ATT_KV_STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = smem + 2 * ATT_TILE_BYTES;
+  uint8_t* sV = sK + NS * ATT_TILE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + NS * ATT_TILE_BYTES);
+  uint64_t* q_full = bars;             // [2]
+  uint64_t* k_full = bars + 2;         // [NS]
+  uint64_t* k_empty = k_full + NS;     // [NS]
+  uint64_t* v_full = k_empty + NS;     // [NS]
+  uint64_t* v_empty = v_full + NS;     // [NS]
+  uint64_t* s_full = v_empty + NS;     // [2]
+  uint64_t* p_full = s_full + 2;       // [2]
+  uint64_t* o_ready = p_full + 2;      // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_ready + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 256;
+  const int head = blockIdx.y;
+  const int bh = blockIdx.z * p.heads + head;
+  const int nkv = (p.n + 127) / 128;
+  const bool two = (q0 + 128) < p.n;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&q_full[i], 1);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 4);
+      mbar_init(&o_ready[i], 1);
+    }
+    for (int i = 0; i < NS; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(&q_full[0], ATT_TILE_BYTES);
+      tma_load_3d(sQ, &tmQ, &q_full[0], 0, q0, bh);
+      if (two) {
+        mbar_expect_tx(&q_full[1], ATT_TILE_BYTES);
+        tma_load_3d(sQ + ATT_TILE_BYTES, &tmQ, &q_full[1], 0, q0 + 128, bh);
+      }
+      int s = 0;
+      uint32_t ph = 0;
+      for (int j = 0; j < nkv; ++j) {
+        mbar_wait(&k_empty[s], ph ^ 1);
+        mbar_expect_tx(&k_full[s], ATT_TILE_BYTES);
+        tma_load_3d(sK + s * ATT_TILE_BYTES, &tmK, &k_full[s], 0, j * 128, bh);
+        mbar_wait(&v_empty[s], ph ^ 1);
+        mbar_expect_tx(&v_full[s], ATT_TILE_BYTES);
+        tma_load_3d(sV + s * ATT_TILE_BYTES, &tmV, &v_full[s], 0, j * 128, bh);
+        if (++s == NS) {
+          s = 0;
+          ph ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
+      constexpr uint32_t idesc_pv = make_idesc_bf16(128, 64, 0, 1);  // B (=V) is MN-major
+      const uint32_t tS[2] = {tmem_base, tmem_base + 128};
+      const uint32_t tO[2] = {tmem_base + 256, tmem_base + 320};
+      auto issue_S = [&](int t, int stage) {
+        const uint64_t adesc = make_sw128_desc(smem_u32(sQ + t * ATT_TILE_BYTES));
+        const uint64_t bdesc = make_sw128_desc(smem_u32(sK + stage * ATT_TILE_BYTES));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_ss(tS[t], adesc + 2 * k, bdesc + 2 * k, idesc_s, k > 0 ? 1u : 0u);
+        umma_commit(&s_full[t]);
+      };
+      auto issue_PV = [&](int t, int stage, int j) {
+        const uint64_t bdesc = make_sw128_desc(smem_u32(sV + stage * ATT_TILE_BYTES));
+#pragma unroll
+        for (int k = 0; k < 8; ++k)   // 16 keys per MMA: P advances 8 cols (bf16x2), V advances 16 rows = 2048 B
+          umma_ts(tO[t], tS[t] + 8 * k, bdesc + static_cast<uint64_t>(k) * (2048 >> 4), idesc_pv,
+                  (j > 0 || k > 0) ? 1u : 0u);
+        umma_commit(&o_ready[t]);
+      };
+      mbar_wait(&q_full[0], 0);
+      mbar_wait(&k_full[0], 0);
+      tc_fence_after();
+      issue_S(0, 0);
+      if (two) {
+        mbar_wait(&q_full[1], 0);
+        tc_fence_after();
+        issue_S(1, 0);
+      }
+      for (int j = 0; j < nkv; ++j) {
+        const int s = j % NS;
+        const uint32_t ph = (j / NS) & 1;
+        const int sn = (j + 1) % NS;
+        const uint32_t phn = ((j + 1) / NS) & 1;
+        const bool more = (j + 1) < nkv;
+        mbar_wait(&v_full[s], ph);
+        mbar_wait(&p_full[0], j & 1);
+        tc_fence_after();
+        issue_PV(0, s, j);
+        if (more) {
+          mbar_wait(&k_full[sn], phn);
+          tc_fence_after();
+          issue_S(0, sn);
+        }
+        if (two) {
+          mbar_wait(&p_full[1], j & 1);
+          tc_fence_after();
+          issue_PV(1, s, j);
+          if (more) issue_S(1, sn);
+        }
+        umma_commit(&v_empty[s]);
+        // K stage j was last read by S_t(j), issued one iteration earlier (or in the prologue): a commit here
+        // covers it.
+        umma_commit(&k_empty[s]);
+      }
+    }
+  } else if (warp >= 4) {
+    const int t = (warp - 4) >> 2;
+    if (t == 0 || two) {
+      const int quarter = warp & 3;
+      const int r = quarter * 32 + lane;
+      const int qrow = q0 + t * 128 + r;
+      const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
+      const uint32_t tS = tmem_base + t * 128 + lane_off;
+      const uint32_t tO = tmem_base + 256 + t * 64 + lane_off;
+      float m_used = -INFINITY;
+      float l = 0.f;
+      for (int j = 0; j < nkv; ++j) {
+        const int kv_valid = min(128, p.n - j * 128);
+        mbar_wait(&s_full[t], j & 1);
+        tc_fence_after();
+        // ---- pass 1: row max
+        float mx = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t raw[32];
+          tmem_ld32(tS + c * 32, raw);
+          tmem_ld_wait();
+          if (kv_valid == 128) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(raw[i]));
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (c * 32 + i < kv_valid) mx = fmaxf(mx, __uint_as_float(raw[i]));
+          }
+        }
+        const float m_new = fmaxf(m_used, mx);
+        if (j == 0) {
+          m_used = m_new;
+        } else {
+          const bool need = (m_new - m_used) > 8.0f;
+          if (__any_sync(0xffffffffu, need)) {
+            mbar_wait(&o_ready[t], (j - 1) & 1);   // PV(j-1) has landed in O
+            tc_fence_after();
+            const float alpha = need ? ex2_approx(m_used - m_new) : 1.0f;
+            if (need) {
+              m_used = m_new;
+              l *= alpha;
+            }
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+              uint32_t o[32];
+              tmem_ld32(tO + c * 32, o);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+              tmem_st32(tO + c * 32, o);
+            }
+            tmem_st_wait();
+          }
+        }
+        // ---- pass 2: P = exp2(S - m), row sum, bf16 pack into the S columns
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t raw[32];
+          tmem_ld32(tS + c * 32, raw);
+          tmem_ld_wait();
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float a = ex2_approx(__uint_as_float(raw[2 * i]) - m_used);
+            float b = ex2_approx(__uint_as_float(raw[2 * i + 1]) - m_used);
+            if (kv_valid != 128) {
+              if (c * 32 + 2 * i >= kv_valid) a = 0.f;
+              if (c * 32 + 2 * i + 1 >= kv_valid) b = 0.f;
+            }
+            l += a + b;
+            pk[i] = pack_bf16(a, b);
+          }
+          tmem_st16(tS + c * 16, pk);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[t]);
+      }
+      // ---- epilogue: O / l -> bf16 -> out[b, qrow, head*64 .. +64)
+      mbar_wait(&o_ready[t], (nkv - 1) & 1);
+      tc_fence_after();
+      const float inv = 1.0f / l;
+      uint32_t o[64];
+      tmem_ld32(tO, o);
+      tmem_ld32(tO + 32, o + 32);
+      tmem_ld_wait();
+      if (qrow < p.n) {
+        uint4* dst = reinterpret_cast<uint4*>(p.out + (static_cast<long long>(blockIdx.z) * p.n + qrow) * p.C +
+                                              head * 64);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          uint4 w;
+          w.x = pack_bf16(__uint_as_float(o[8 * i + 0]) * inv, __uint_as_float(o[8 * i + 1]) * inv);
+          w.y = pack_bf16(__uint_as_float(o[8 * i + 2]) * inv, __uint_as_float(o[8 * i + 3]) * inv);
+          w.z = pack_bf16(__uint_as_float(o[8 * i + 4]) * inv, __uint_as_float(o[8 * i + 5]) * inv);
+          w.w = pack_bf16(__uint_as_float(o[8 * i + 6]) * inv, __uint_as_float(o[8 * i + 7]) * inv);
+          dst[i] = w;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace ovg

@@ -1,0 +1,319 @@
+// HBM-bound kernels of the hot path: LayerNorm, token assembly / modality scatter, camera-token injection,
+// intermediate snapshots, depth normalisation + im2col, strided-conv im2col, bilinear upsampling.
+// All use 16-byte vectorised, coalesced accesses; none reshapes work into GEMMs.
+#pragma once
+#include "ptx.cuh"
+
+namespace ovg {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// LayerNorm over the last dim (reference layers/block.py:50,:67 norm1/norm2; heads/dpt_head.py:66,:227).
+// One warp per row; fp32 or bf16 input, bf16 output, optional affine.  Row gather: output row m reads
+// input row (m / grp_out) * grp_in + grp_off + (m % grp_out)   (grp_out == 0 -> identity); this drops the 5
+// special tokens of every frame for the DPT input (heads/dpt_head.py:219).
+struct LnParams {
+  const void* in;
+  int in_bf16;
+  long long ld_in;
+  __nv_bfloat16* out;
+  long long ld_out;
+  int rows, C;
+  const float* w;
+  const float* b;
+  float eps;
+  int grp_out, grp_in, grp_off;
+};
+
+template <int VPL>  // values per lane = C / 32 (multiple of 4)
+__global__ void __launch_bounds__(256) layernorm_kernel(const LnParams p) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= p.rows) return;
+  long long src = warp;
+  if (p.grp_out > 0) src = static_cast<long long>(warp / p.grp_out) * p.grp_in + p.grp_off + (warp % p.grp_out);
+  float v[VPL];
+  // lane handles chunks of 4 consecutive elements: element index = (i*32 + lane)*4 + e
+  if (p.in_bf16) {
+    const __nv_bfloat16* x = reinterpret_cast<const __nv_bfloat16*>(p.in) + src * p.ld_in;
+#pragma unroll
+    for (int i = 0; i < VPL / 4; ++i) {
+      const uint2 u = *reinterpret_cast<const uint2*>(x + (i * 32 + lane) * 4);
+      v[4 * i + 0] = bf16_lo(u.x);
+      v[4 * i + 1] = bf16_hi(u.x);
+      v[4 * i + 2] = bf16_lo(u.y);
+      v[4 * i + 3] = bf16_hi(u.y);
+    }
+  } else {
+    const float* x = reinterpret_cast<const float*>(p.in) + src * p.ld_in;
+#pragma unroll
+    for (int i = 0; i < VPL / 4; ++i) {
+      const float4 f = *reinterpret_cast<const float4*>(x + (i * 32 + lane) * 4);
+      v[4 * i + 0] = f.x;
+      v[4 * i + 1] = f.y;
+      v[4 * i + 2] = f.z;
+      v[4 * i + 3] = f.w;
+    }
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) s += v[i];
+  const float mean = warp_sum(s) / p.C;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const float d = v[i] - mean;
+    q += d * d;
+  }
+  const float rstd = rsqrtf(warp_sum(q) / p.C + p.eps);
+  __nv_bfloat16* y = p.out + static_cast<long long>(warp) * p.ld_out;
+#pragma unroll
+  for (int i = 0; i < VPL / 4; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    float o[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      o[e] = (v[4 * i + e] - mean) * rstd;
+      if (p.w) o[e] = o[e] * __ldg(p.w + c + e) + __ldg(p.b + c + e);
+    }
+    uint2 u;
+    u.x = pack_bf16(o[0], o[1]);
+    u.y = pack_bf16(o[2], o[3]);
+    *reinterpret_cast<uint2*>(y + c) = u;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Token assembly (reference omnivggt_aggregator.py:155-156,:211-213 + aggregator.py:343-366).
+//   x[k,0]       = camera_token[slot(k)] + inj0[k]              (inj0 = camera_adapters[0](g0), bias on ALL frames)
+//   x[k,1..R]    = register_token[slot(k)]
+//   x[k,R+1+p]   = patch[k,p] + (has_depth[k] ? 0 : depth_placeholder)   (selected frames get their depth
+//                  tokens added by the depth-embedding GEMM epilogue, see ovg_gemm EPI_RESID + row_index)
+// slot(k) = 0 for the first view of a scene, 1 otherwise.  One block per token row, float4 per thread.
+struct AssembleParams {
+  float* x;             // [K, T, C]
+  const float* patch;   // [K, P, C]
+  const float* cam_tok;  // [2, C]
+  const float* reg_tok;  // [2, R, C]
+  const float* inj0;     // [K, C]
+  const float* placeholder;  // [C]
+  const int* has_depth;      // [K]
+  int K, S, T, R, C;
+};
+
+__global__ void assemble_tokens_kernel(const AssembleParams p) {
+  const int row = blockIdx.x;
+  const int k = row / p.T, t = row % p.T;
+  const int slot = (k % p.S) == 0 ? 0 : 1;
+  const int P = p.T - p.R - 1;
+  for (int c = threadIdx.x * 4; c < p.C; c += blockDim.x * 4) {
+    float4 o;
+    if (t == 0) {
+      const float4 a = *reinterpret_cast<const float4*>(p.cam_tok + slot * p.C + c);
+      const float4 b = *reinterpret_cast<const float4*>(p.inj0 + static_cast<long long>(k) * p.C + c);
+      o = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+    } else if (t <= p.R) {
+      o = *reinterpret_cast<const float4*>(p.reg_tok + (static_cast<long long>(slot) * p.R + (t - 1)) * p.C + c);
+    } else {
+      o = *reinterpret_cast<const float4*>(p.patch + (static_cast<long long>(k) * P + (t - 1 - p.R)) * p.C + c);
+      if (!p.has_depth[k]) {
+        const float4 d = *reinterpret_cast<const float4*>(p.placeholder + c);
+        o.x += d.x; o.y += d.y; o.z += d.z; o.w += d.w;
+      }
+    }
+    *reinterpret_cast<float4*>(p.x + static_cast<long long>(row) * p.C + c) = o;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Per-layer camera injection + intermediate snapshot (reference omnivggt_aggregator.py:273-303,:248-251).
+//   x[k,0,:] += inj[k,:]                                   (only token 0 of each frame receives a non-zero add)
+//   slot[k,t, coff:coff+C] = bf16(x[k,t,:])                (frame half coff=0 / global half coff=C)
+//   cam_out[k, coff:coff+C] = x[k,0,:]                     (fp32 camera tokens for the camera head)
+struct InjectParams {
+  float* x;                 // [K*T, C]
+  const float* inj;         // [K, C] or nullptr
+  __nv_bfloat16* slot;      // [K*T, 2C] or nullptr
+  float* cam_out;           // [K, 2C] or nullptr
+  int K, T, C, coff;
+};
+
+__global__ void inject_snapshot_kernel(const InjectParams p) {
+  const int row = blockIdx.x;
+  const int k = row / p.T, t = row % p.T;
+  if (!p.slot && t != 0) return;
+  for (int c = threadIdx.x * 4; c < p.C; c += blockDim.x * 4) {
+    float4 v = *reinterpret_cast<const float4*>(p.x + static_cast<long long>(row) * p.C + c);
+    if (t == 0) {
+      if (p.inj) {
+        const float4 a = *reinterpret_cast<const float4*>(p.inj + static_cast<long long>(k) * p.C + c);
+        v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+        *reinterpret_cast<float4*>(p.x + static_cast<long long>(row) * p.C + c) = v;
+      }
+      if (p.cam_out) *reinterpret_cast<float4*>(p.cam_out + static_cast<long long>(k) * 2 * p.C + p.coff + c) = v;
+    }
+    if (p.slot) {
+      uint2 u;
+      u.x = pack_bf16(v.x, v.y);
+      u.y = pack_bf16(v.z, v.w);
+      *reinterpret_cast<uint2*>(p.slot + static_cast<long long>(row) * 2 * p.C + p.coff + c) = u;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Depth modality (reference omnivggt_aggregator.py:107-128,:189-199): per-scene masked mean over the
+// selected views, then im2col of [depth/(mean+eps)*mask, mask] into rows of 2*14*14 for the 14x14/s14
+// patch-embedding GEMM.  Two deterministic stages (no float atomics).
+struct DepthParams {
+  const float* depth;  // [B, S, H, W]
+  const float* mask;   // [B, S, H, W]
+  const int* idx;      // [Sd] selected views
+  double* partial;     // [B, NCHUNK, 2] (sum, count)
+  __nv_bfloat16* cols;  // [B*Sd*hp*wp, ldc]
+  int ldc;
+  int B, S, Sd, H, W, patch;
+};
+constexpr int DEPTH_NCHUNK = 128;
+
+__global__ void __launch_bounds__(256) depth_stats_kernel(const DepthParams p) {
+  const int b = blockIdx.y, ch = blockIdx.x;
+  const long long per = static_cast<long long>(p.H) * p.W;
+  const long long total = per * p.Sd;
+  double s = 0.0, cnt = 0.0;
+  for (long long i = static_cast<long long>(ch) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(DEPTH_NCHUNK) * blockDim.x) {
+    const int j = static_cast<int>(i / per);
+    const long long off = (static_cast<long long>(b) * p.S + p.idx[j]) * per + (i - j * per);
+    if (p.mask[off] > 0.f) {
+      s += p.depth[off];
+      cnt += 1.0;
+    }
+  }
+  __shared__ double sh[2][256];
+  sh[0][threadIdx.x] = s;
+  sh[1][threadIdx.x] = cnt;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      sh[0][threadIdx.x] += sh[0][threadIdx.x + o];
+      sh[1][threadIdx.x] += sh[1][threadIdx.x + o];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    p.partial[(static_cast<long long>(b) * DEPTH_NCHUNK + ch) * 2 + 0] = sh[0][0];
+    p.partial[(static_cast<long long>(b) * DEPTH_NCHUNK + ch) * 2 + 1] = sh[1][0];
+  }
+}
+
+__global__ void __launch_bounds__(224) depth_im2col_kernel(const DepthParams p) {
+  const int hp = p.H / p.patch, wp = p.W / p.patch;
+  const int row = blockIdx.x;  // (b, j, py, px)
+  const int px = row % wp, py = (row / wp) % hp, j = (row / (wp * hp)) % p.Sd, b = row / (wp * hp * p.Sd);
+  __shared__ float s_scale;
+  if (threadIdx.x == 0) {
+    double s = 0.0, c = 0.0;
+    for (int i = 0; i < DEPTH_NCHUNK; ++i) {
+      s += p.partial[(static_cast<long long>(b) * DEPTH_NCHUNK + i) * 2 + 0];
+      c += p.partial[(static_cast<long long>(b) * DEPTH_NCHUNK + i) * 2 + 1];
+    }
+    s_scale = c > 0.0 ? 1.0f / (static_cast<float>(s / c) + 1e-8f) : 0.0f;   // no valid pixel -> zeros (:121-122)
+  }
+  __syncthreads();
+  const int pp = p.patch * p.patch;
+  for (int e = threadIdx.x; e < pp; e += blockDim.x) {
+    const int ky = e / p.patch, kx = e % p.patch;
+    const long long off = ((static_cast<long long>(b) * p.S + p.idx[j]) * p.H + (py * p.patch + ky)) * p.W +
+                          (px * p.patch + kx);
+    const float m = p.mask[off];
+    const float d = p.depth[off] * s_scale * m;
+    __nv_bfloat16* dst = p.cols + static_cast<long long>(row) * p.ldc;
+    dst[e] = __float2bfloat16(d);
+    dst[pp + e] = __float2bfloat16(m);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// im2col for the stride-2 3x3 conv of DPT level 4 (reference heads/dpt_head.py:93-95): dense NHWC
+// [F,h,w,C] -> rows (f,oy,ox) x cols (tap, c).  One block per (output pixel, tap); uint4 copies.
+struct Im2colParams {
+  const __nv_bfloat16* src;  // [F, h, w, C]
+  __nv_bfloat16* dst;        // [F*oh*ow, 9*C]
+  int F, h, w, C, oh, ow;
+};
+
+__global__ void im2col3x3s2_kernel(const Im2colParams p) {
+  const int tap = blockIdx.y;
+  const int pix = blockIdx.x;
+  const int ox = pix % p.ow, oy = (pix / p.ow) % p.oh, f = pix / (p.ow * p.oh);
+  const int iy = 2 * oy + tap / 3 - 1, ix = 2 * ox + tap % 3 - 1;
+  const bool ok = iy >= 0 && iy < p.h && ix >= 0 && ix < p.w;
+  const uint4* s = reinterpret_cast<const uint4*>(p.src + ((static_cast<long long>(f) * p.h + iy) * p.w + ix) * p.C);
+  uint4* d = reinterpret_cast<uint4*>(p.dst + (static_cast<long long>(pix) * 9 + tap) * p.C);
+  for (int c = threadIdx.x; c < p.C / 8; c += blockDim.x) d[c] = ok ? s[c] : make_uint4(0, 0, 0, 0);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Bilinear upsampling, align_corners=True (reference heads/dpt_head.py:466,:472-497, F.interpolate), on
+// zero-bordered NHWC bf16 maps: src [F,h+2,w+2,C] -> dst [F,H+2,W+2,C]; optional fp32 additive table
+// [H*W, C] (the x0.1 UV position embedding of heads/dpt_head.py:249-250).  Border pixels are written as 0.
+struct UpsampleParams {
+  const __nv_bfloat16* src;
+  __nv_bfloat16* dst;
+  const float* table;
+  int F, h, w, H, W, C;
+};
+
+__global__ void __launch_bounds__(256) upsample_bilinear_kernel(const UpsampleParams p) {
+  const int vec = p.C / 8;
+  const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long pix = gid / vec;
+  const int cv = static_cast<int>(gid % vec);
+  const long long npix = static_cast<long long>(p.F) * (p.H + 2) * (p.W + 2);
+  if (pix >= npix) return;
+  const int X = static_cast<int>(pix % (p.W + 2));
+  const int Y = static_cast<int>((pix / (p.W + 2)) % (p.H + 2));
+  const int f = static_cast<int>(pix / (static_cast<long long>(p.W + 2) * (p.H + 2)));
+  uint4 out = make_uint4(0, 0, 0, 0);
+  if (X >= 1 && X <= p.W && Y >= 1 && Y <= p.H) {
+    const int oy = Y - 1, ox = X - 1;
+    const float sy = p.H > 1 ? static_cast<float>(p.h - 1) / static_cast<float>(p.H - 1) : 0.f;
+    const float sx = p.W > 1 ? static_cast<float>(p.w - 1) / static_cast<float>(p.W - 1) : 0.f;
+    const float fy = sy * oy, fx = sx * ox;
+    const int y0 = static_cast<int>(fy), x0 = static_cast<int>(fx);
+    const int y1 = y0 + (y0 < p.h - 1 ? 1 : 0), x1 = x0 + (x0 < p.w - 1 ? 1 : 0);
+    const float wy1 = fy - y0, wx1 = fx - x0;
+    const float wy0 = 1.f - wy1, wx0 = 1.f - wx1;
+    const long long base = static_cast<long long>(f) * (p.h + 2) * (p.w + 2);
+    auto ld = [&](int yy, int xx) {
+      return __ldg(reinterpret_cast<const uint4*>(p.src + (base + static_cast<long long>(yy + 1) * (p.w + 2) + (xx + 1)) * p.C) + cv);
+    };
+    const uint4 a = ld(y0, x0), b = ld(y0, x1), c = ld(y1, x0), d = ld(y1, x1);
+    const uint32_t* ap = &a.x; const uint32_t* bp = &b.x; const uint32_t* cp = &c.x; const uint32_t* dp = &d.x;
+    float r[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      r[2 * i] = wy0 * (wx0 * bf16_lo(ap[i]) + wx1 * bf16_lo(bp[i])) + wy1 * (wx0 * bf16_lo(cp[i]) + wx1 * bf16_lo(dp[i]));
+      r[2 * i + 1] = wy0 * (wx0 * bf16_hi(ap[i]) + wx1 * bf16_hi(bp[i])) + wy1 * (wx0 * bf16_hi(cp[i]) + wx1 * bf16_hi(dp[i]));
+    }
+    if (p.table) {
+      const float4* t = reinterpret_cast<const float4*>(p.table + (static_cast<long long>(oy) * p.W + ox) * p.C + cv * 8);
+      const float4 t0 = __ldg(t), t1 = __ldg(t + 1);
+      r[0] += t0.x; r[1] += t0.y; r[2] += t0.z; r[3] += t0.w;
+      r[4] += t1.x; r[5] += t1.y; r[6] += t1.z; r[7] += t1.w;
+    }
+    out.x = pack_bf16(r[0], r[1]);
+    out.y = pack_bf16(r[2], r[3]);
+    out.z = pack_bf16(r[4], r[5]);
+    out.w = pack_bf16(r[6], r[7]);
+  }
+  *(reinterpret_cast<uint4*>(p.dst + pix * p.C) + cv) = out;
+}
+
+}  // namespace ovg

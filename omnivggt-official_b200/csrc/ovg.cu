@@ -1,0 +1,362 @@
+// libovg C ABI (include/ovg.h): argument validation, TMA descriptor cache, kernel launches.
+#include <atomic>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+
+#include <cudaTypedefs.h>
+
+#include "../../include/ovg.h"
+#include "attn.cuh"
+#include "elem.cuh"
+#include "gemm.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<long long> g_launches{0};
+
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+
+#define OVG_REQUIRE(cond, msg)                                                           \
+  do {                                                                                   \
+    if (!(cond)) return fail(OVG_E_INVALID, std::string(__func__) + ": " + (msg));        \
+  } while (0)
+
+#define OVG_CUDA(expr)                                                                   \
+  do {                                                                                   \
+    cudaError_t e__ = (expr);                                                            \
+    if (e__ != cudaSuccess)                                                              \
+      return fail(OVG_E_CUDA, std::string(__func__) + ": " #expr ": " + cudaGetErrorString(e__)); \
+  } while (0)
+
+int post_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(OVG_E_CUDA, std::string(what) + ": launch failed: " + cudaGetErrorString(e));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return OVG_OK;
+}
+
+// ------------------------------------------------------------------------------ tensor maps
+PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess) p = nullptr;
+    return reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  }();
+  return fn;
+}
+
+struct MapKey {
+  const void* ptr;
+  unsigned long long d0, d1, d2, ld, box1;
+  bool operator==(const MapKey& o) const {
+    return ptr == o.ptr && d0 == o.d0 && d1 == o.d1 && d2 == o.d2 && ld == o.ld && box1 == o.box1;
+  }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    size_t h = std::hash<const void*>()(k.ptr);
+    for (unsigned long long v : {k.d0, k.d1, k.d2, k.ld, k.box1}) h = h * 1000003u ^ std::hash<unsigned long long>()(v);
+    return h;
+  }
+};
+std::mutex g_map_mu;
+std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
+
+// bf16 tensor [d2][d1][d0] (d0 contiguous, row stride ld elements, d2 stride d1*ld), box = [64, box1, 1], 128B swizzle.
+// d2 == 0 -> rank 2.
+int get_map(const void* ptr, unsigned long long d0, unsigned long long d1, unsigned long long d2,
+            unsigned long long ld, unsigned box1, CUtensorMap* out) {
+  MapKey key{ptr, d0, d1, d2, ld, box1};
+  {
+    std::lock_guard<std::mutex> g(g_map_mu);
+    auto it = g_maps.find(key);
+    if (it != g_maps.end()) {
+      *out = it->second;
+      return OVG_OK;
+    }
+  }
+  auto enc = get_encode();
+  if (!enc) return fail(OVG_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || ((ld * 2) & 15))
+    return fail(OVG_E_INVALID, "TMA operand must be 16-byte aligned with a 16-byte multiple row stride");
+  cuuint64_t gdim[3] = {d0, d1, d2 ? d2 : 1};
+  cuuint64_t gstr[2] = {ld * 2, d1 * ld * 2};
+  cuuint32_t box[3] = {64, box1, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUtensorMap m;
+  CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, d2 ? 3 : 2, const_cast<void*>(ptr), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(OVG_E_CUDA, "cuTensorMapEncodeTiled failed (" + std::to_string(int(r)) + ")");
+  {
+    std::lock_guard<std::mutex> g(g_map_mu);
+    if (g_maps.size() > 8192) g_maps.clear();
+    g_maps.emplace(key, m);
+  }
+  *out = m;
+  return OVG_OK;
+}
+
+int num_sms() {
+  static int n = [] {
+    int dev = 0, v = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    return v;
+  }();
+  return n;
+}
+
+template <int BN, int EPI>
+int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const ovg::GemmParams& p, cudaStream_t st) {
+  using Cfg = ovg::GemmCfg<BN>;
+  static bool attr_set = false;
+  auto kern = ovg::gemm_kernel<BN, EPI>;
+  if (!attr_set) {
+    OVG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int tiles = ((p.M + 127) / 128) * ((p.N + BN - 1) / BN);
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  kern<<<grid, ovg::GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, p);
+  return post_launch("ovg_gemm");
+}
+
+template <int EPI>
+int dispatch_bn(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const ovg::GemmParams& p, cudaStream_t st) {
+  switch (bn) {
+    case 256: return launch_gemm<256, EPI>(ta, tb, p, st);
+    case 128: return launch_gemm<128, EPI>(ta, tb, p, st);
+    case 64: return launch_gemm<64, EPI>(ta, tb, p, st);
+    default: return fail(OVG_E_INVALID, "ovg_gemm: unsupported block_n");
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int ovg_version(void) { return 1; }
+const char* ovg_last_error(void) { return g_err.c_str(); }
+long long ovg_launch_count(void) { return g_launches.load(); }
+
+int ovg_device_check(void) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return fail(OVG_E_NODEVICE, "no CUDA device");
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return fail(OVG_E_NODEVICE, "cannot query device");
+  if (prop.major != 10)
+    return fail(OVG_E_NODEVICE, std::string("libovg requires sm_100 (B200); found sm_") + std::to_string(prop.major) +
+                                    std::to_string(prop.minor));
+  return OVG_OK;
+}
+
+int ovg_gemm(const ovg_gemm_args* a, void* stream) {
+  OVG_REQUIRE(a && a->a && a->b, "null operand");
+  OVG_REQUIRE(a->m > 0 && a->n > 0 && a->a_cols > 0 && a->a_rows > 0, "empty problem");
+  OVG_REQUIRE(a->num_taps >= 1 && a->num_taps <= 9, "num_taps must be in [1,9]");
+  OVG_REQUIRE(a->a_cols % 8 == 0, "a_cols must be a multiple of 8");
+  OVG_REQUIRE(a->num_taps == 1 || a->a_cols % 64 == 0, "multi-tap GEMM needs a_cols % 64 == 0");
+  OVG_REQUIRE(a->n % 32 == 0, "n must be a multiple of 32");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+
+  ovg::GemmParams p{};
+  p.M = a->m;
+  p.N = a->n;
+  p.kc_blocks = (a->a_cols + 63) / 64;
+  p.k_blocks = p.kc_blocks * a->num_taps;
+  for (int i = 0; i < 9; ++i) p.tap_off[i] = i < a->num_taps ? a->tap_off[i] : 0;
+  p.bias = a->bias;
+  p.act = a->act;
+  p.out = a->out;
+  p.ldo = a->ldo;
+  p.table = a->table;
+  p.table_rows = a->table_rows > 0 ? a->table_rows : 1;
+  p.skip1 = reinterpret_cast<const __nv_bfloat16*>(a->skip1);
+  p.skip2 = reinterpret_cast<const __nv_bfloat16*>(a->skip2);
+  p.rowmap = a->rowmap;
+  p.gh = a->gh;
+  p.gw = a->gw;
+  p.ps = a->ps;
+  p.cout = a->cout;
+  p.gamma = a->gamma;
+  p.row_index = a->row_index;
+  p.q_out = reinterpret_cast<__nv_bfloat16*>(a->q_out);
+  p.k_out = reinterpret_cast<__nv_bfloat16*>(a->k_out);
+  p.v_out = reinterpret_cast<__nv_bfloat16*>(a->v_out);
+  p.C = a->C;
+  p.ntok = a->ntok;
+  p.T = a->T;
+  p.nspecial = a->nspecial;
+  p.wp = a->wp;
+  p.maxpos = a->maxpos;
+  p.qn_w = a->qn_w;
+  p.qn_b = a->qn_b;
+  p.kn_w = a->kn_w;
+  p.kn_b = a->kn_b;
+  p.rope_cos = a->rope_cos;
+  p.rope_sin = a->rope_sin;
+  p.qscale = a->qscale;
+  p.w2 = a->w2;
+  p.b2 = a->b2;
+  p.outc = a->outc;
+  p.head_act = a->head_act;
+  p.preds = a->preds;
+  p.conf = a->conf;
+
+  int bn = a->block_n;
+  if (a->epi == OVG_EPI_HEADTAIL) {
+    OVG_REQUIRE(a->n == 32, "HEADTAIL epilogue needs n == 32");
+    OVG_REQUIRE(a->w2 && a->b2 && a->bias && a->preds && a->conf && a->outc >= 2 && a->outc <= 4, "HEADTAIL args");
+    OVG_REQUIRE(a->rowmap == OVG_ROWS_PAD, "HEADTAIL runs on the zero-bordered grid");
+    bn = 32;
+  } else if (bn == 0) {
+    bn = a->n >= 256 ? 256 : (a->n >= 128 ? 128 : 64);
+    if (a->epi != OVG_EPI_QKV && bn == 256) {
+      // prefer 128-wide tiles when 256-wide ones leave a badly quantised last wave
+      const long long mt = (a->m + 127) / 128;
+      const long long t256 = mt * ((a->n + 255) / 256), t128 = mt * ((a->n + 127) / 128);
+      const int sms = num_sms();
+      const double e256 = double(t256) / double(((t256 + sms - 1) / sms) * sms);
+      const double e128 = double(t128) / double(((t128 + sms - 1) / sms) * sms);
+      if (e128 > e256 + 0.08) bn = 128;
+    }
+  }
+  if (a->epi == OVG_EPI_QKV) {
+    OVG_REQUIRE(a->q_out && a->k_out && a->v_out && a->bias && a->qn_w && a->qn_b && a->kn_w && a->kn_b, "QKV args");
+    OVG_REQUIRE(a->rope_cos && a->rope_sin && a->maxpos > 0 && a->maxpos <= 64, "QKV rope table (maxpos <= 64)");
+    OVG_REQUIRE(a->C % 64 == 0 && a->n == 3 * a->C && a->ntok > 0 && a->T > 0 && a->wp > 0, "QKV geometry");
+    OVG_REQUIRE(a->m % a->ntok == 0, "m must be a multiple of ntok");
+    if (bn < 64) bn = 64;
+  } else if (a->epi == OVG_EPI_RESID) {
+    OVG_REQUIRE(a->out && a->gamma && a->bias, "RESID needs out, gamma, bias");
+  } else if (a->epi == OVG_EPI_BF16) {
+    OVG_REQUIRE(a->out, "BF16 epilogue needs out");
+    if (a->rowmap == OVG_ROWS_PIXSHUF)
+      OVG_REQUIRE(a->ps > 0 && a->cout % 32 == 0 && a->n == a->ps * a->ps * a->cout, "PIXSHUF geometry");
+    if (a->rowmap != OVG_ROWS_IDENT) OVG_REQUIRE(a->gh > 0 && a->gw > 0, "row map needs gh, gw");
+  }
+
+  CUtensorMap ta, tb;
+  int rc = get_map(a->a, a->a_cols, a->a_rows, 0, a->lda, 128, &ta);
+  if (rc) return rc;
+  const unsigned long long ktot = static_cast<unsigned long long>(a->a_cols) * a->num_taps;
+  rc = get_map(a->b, ktot, a->n, 0, a->ldb, bn, &tb);
+  if (rc) return rc;
+
+  switch (a->epi) {
+    case OVG_EPI_BF16: return dispatch_bn<ovg::EPI_BF16>(bn, ta, tb, p, st);
+    case OVG_EPI_RESID: return dispatch_bn<ovg::EPI_RESID>(bn, ta, tb, p, st);
+    case OVG_EPI_QKV: return dispatch_bn<ovg::EPI_QKV>(bn, ta, tb, p, st);
+    case OVG_EPI_HEADTAIL: return launch_gemm<32, ovg::EPI_HEADTAIL>(ta, tb, p, st);
+    default: return fail(OVG_E_INVALID, "ovg_gemm: unknown epilogue");
+  }
+}
+
+int ovg_attention(const void* q, const void* k, const void* v, void* out, int batch, int heads, int n, void* stream) {
+  OVG_REQUIRE(q && k && v && out, "null operand");
+  OVG_REQUIRE(batch > 0 && heads > 0 && n > 0, "empty problem");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  CUtensorMap tq, tk, tv;
+  const unsigned long long bh = static_cast<unsigned long long>(batch) * heads;
+  int rc = get_map(q, 64, n, bh, 64, 128, &tq);
+  if (rc) return rc;
+  rc = get_map(k, 64, n, bh, 64, 128, &tk);
+  if (rc) return rc;
+  rc = get_map(v, 64, n, bh, 64, 128, &tv);
+  if (rc) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    OVG_CUDA(cudaFuncSetAttribute(ovg::attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ovg::ATT_SMEM_BYTES));
+    attr_set = true;
+  }
+  ovg::AttnParams p{n, heads, heads * 64, reinterpret_cast<__nv_bfloat16*>(out)};
+  dim3 grid((n + 255) / 256, heads, batch);
+  ovg::attn_kernel<<<grid, ovg::ATT_THREADS, ovg::ATT_SMEM_BYTES, st>>>(tq, tk, tv, p);
+  return post_launch("ovg_attention");
+}
+
+int ovg_layernorm(const void* in, int in_is_bf16, long long ld_in, void* out, long long ld_out, int rows, int C,
+                  const float* w, const float* b, float eps, int grp_out, int grp_in, int grp_off, void* stream) {
+  OVG_REQUIRE(in && out && rows > 0, "null operand");
+  OVG_REQUIRE((w == nullptr) == (b == nullptr), "affine needs both weight and bias");
+  OVG_REQUIRE(C % 128 == 0 && C <= 2048, "C must be a multiple of 128, <= 2048");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  ovg::LnParams p{in, in_is_bf16, ld_in, reinterpret_cast<__nv_bfloat16*>(out), ld_out, rows, C, w, b, eps,
+                  grp_out, grp_in, grp_off};
+  const int blocks = (rows + 7) / 8;
+  switch (C / 32) {
+#define OVG_LN_CASE(V) \
+  case V: ovg::layernorm_kernel<V><<<blocks, 256, 0, st>>>(p); break;
+    OVG_LN_CASE(4) OVG_LN_CASE(8) OVG_LN_CASE(12) OVG_LN_CASE(16) OVG_LN_CASE(20) OVG_LN_CASE(24) OVG_LN_CASE(28)
+    OVG_LN_CASE(32) OVG_LN_CASE(36) OVG_LN_CASE(40) OVG_LN_CASE(44) OVG_LN_CASE(48) OVG_LN_CASE(52) OVG_LN_CASE(56)
+    OVG_LN_CASE(60) OVG_LN_CASE(64)
+#undef OVG_LN_CASE
+    default: return fail(OVG_E_INVALID, "ovg_layernorm: unsupported C");
+  }
+  return post_launch("ovg_layernorm");
+}
+
+int ovg_assemble_tokens(float* x, const float* patch, const float* cam_tok, const float* reg_tok, const float* inj0,
+                        const float* placeholder, const int* has_depth, int K, int S, int T, int R, int C,
+                        void* stream) {
+  OVG_REQUIRE(x && patch && cam_tok && reg_tok && inj0 && placeholder && has_depth, "null operand");
+  OVG_REQUIRE(K > 0 && S > 0 && K % S == 0 && T > R + 1 && C % 4 == 0, "bad geometry");
+  ovg::AssembleParams p{x, patch, cam_tok, reg_tok, inj0, placeholder, has_depth, K, S, T, R, C};
+  const int threads = C / 4 < 256 ? ((C / 4 + 31) / 32) * 32 : 256;
+  ovg::assemble_tokens_kernel<<<K * T, threads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  return post_launch("ovg_assemble_tokens");
+}
+
+int ovg_inject_snapshot(float* x, const float* inj, void* slot, float* cam_out, int K, int T, int C, int coff,
+                        void* stream) {
+  OVG_REQUIRE(x && K > 0 && T > 0 && C % 4 == 0, "bad arguments");
+  OVG_REQUIRE(coff == 0 || coff == C, "coff must be 0 or C");
+  ovg::InjectParams p{x, inj, reinterpret_cast<__nv_bfloat16*>(slot), cam_out, K, T, C, coff};
+  const int threads = C / 4 < 256 ? ((C / 4 + 31) / 32) * 32 : 256;
+  ovg::inject_snapshot_kernel<<<K * T, threads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  return post_launch("ovg_inject_snapshot");
+}
+
+int ovg_depth_im2col(const float* depth, const float* mask, const int* idx, double* scratch, void* cols, int ldc,
+                     int B, int S, int Sd, int H, int W, int patch, void* stream) {
+  OVG_REQUIRE(depth && mask && idx && scratch && cols, "null operand");
+  OVG_REQUIRE(B > 0 && Sd > 0 && Sd <= S && H % patch == 0 && W % patch == 0, "bad geometry");
+  OVG_REQUIRE(ldc >= 2 * patch * patch, "ldc too small");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  ovg::DepthParams p{depth, mask, idx, scratch, reinterpret_cast<__nv_bfloat16*>(cols), ldc, B, S, Sd, H, W, patch};
+  ovg::depth_stats_kernel<<<dim3(ovg::DEPTH_NCHUNK, B), 256, 0, st>>>(p);
+  int rc = post_launch("ovg_depth_im2col(stats)");
+  if (rc) return rc;
+  const int rows = B * Sd * (H / patch) * (W / patch);
+  ovg::depth_im2col_kernel<<<rows, 224, 0, st>>>(p);
+  return post_launch("ovg_depth_im2col");
+}
+
+int ovg_im2col3x3s2(const void* src, void* dst, int F, int h, int w, int C, void* stream) {
+  OVG_REQUIRE(src && dst && F > 0 && h > 0 && w > 0 && C % 8 == 0, "bad arguments");
+  const int oh = (h - 1) / 2 + 1, ow = (w - 1) / 2 + 1;
+  ovg::Im2colParams p{reinterpret_cast<const __nv_bfloat16*>(src), reinterpret_cast<__nv_bfloat16*>(dst), F, h, w, C, oh, ow};
+  const int threads = C / 8 < 128 ? ((C / 8 + 31) / 32) * 32 : 128;
+  ovg::im2col3x3s2_kernel<<<dim3(F * oh * ow, 9), threads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  return post_launch("ovg_im2col3x3s2");
+}
+
+int ovg_upsample_bilinear(const void* src, void* dst, const float* table, int F, int h, int w, int H, int W, int C,
+                          void* stream) {
+  OVG_REQUIRE(src && dst && F > 0 && h > 0 && w > 0 && H > 0 && W > 0 && C % 8 == 0, "bad arguments");
+  ovg::UpsampleParams p{reinterpret_cast<const __nv_bfloat16*>(src), reinterpret_cast<__nv_bfloat16*>(dst), table,
+                        F, h, w, H, W, C};
+  const long long total = static_cast<long long>(F) * (H + 2) * (W + 2) * (C / 8);
+  const long long blocks = (total + 255) / 256;
+  ovg::upsample_bilinear_kernel<<<static_cast<unsigned>(blocks), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  return post_launch("ovg_upsample_bilinear");
+}
+
+}  // extern "C"

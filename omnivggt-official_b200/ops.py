@@ -1,0 +1,116 @@
+"""Thin tensor-level wrappers over the libovg C ABI (device pointers + current stream).  Pure plumbing:
+argument checking and pointer extraction; every byte of arithmetic happens in the CUDA library."""
+from __future__ import annotations
+
+import math
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib as L
+
+BF16 = torch.bfloat16
+F32 = torch.float32
+
+
+def _chk(t: torch.Tensor, dtype, name: str):
+    if t.dtype != dtype or not t.is_cuda:
+        raise TypeError(f"{name}: expected cuda {dtype}, got {t.device} {t.dtype}")
+
+
+def gemm(a: torch.Tensor, b: torch.Tensor, *, m: Optional[int] = None, taps: Optional[Sequence[int]] = None,
+         epi: int = L.EPI_BF16, block_n: int = 0, **kw) -> None:
+    """a: bf16 [rows, a_cols] (last dim contiguous), b: bf16 [n, taps*a_cols].  kw: fields of ovg_gemm_args."""
+    _chk(a, BF16, "a")
+    _chk(b, BF16, "b")
+    assert a.dim() == 2 and b.dim() == 2 and a.stride(1) == 1 and b.stride(1) == 1
+    taps = list(taps) if taps is not None else [0]
+    assert b.shape[1] == a.shape[1] * len(taps), (tuple(a.shape), tuple(b.shape), len(taps))
+    g = L.GemmArgs()
+    g.a, g.a_rows, g.a_cols, g.lda = a.data_ptr(), a.shape[0], a.shape[1], a.stride(0)
+    g.b, g.n, g.ldb = b.data_ptr(), b.shape[0], b.stride(0)
+    g.m = a.shape[0] if m is None else m
+    g.num_taps = len(taps)
+    for i, t in enumerate(taps):
+        g.tap_off[i] = int(t)
+    g.epi = epi
+    g.block_n = block_n
+    keep = []
+    for k, v in kw.items():
+        if isinstance(v, torch.Tensor):
+            assert v.is_cuda and v.is_contiguous(), k
+            keep.append(v)
+            setattr(g, k, v.data_ptr())
+        elif v is not None:
+            setattr(g, k, v)
+    L.check(L.lib().ovg_gemm(g, L.stream()))
+
+
+def linear_bf16(a, w, bias=None, act=L.ACT_NONE, out=None, block_n=0):
+    out = out if out is not None else torch.empty(a.shape[0], w.shape[0], device=a.device, dtype=BF16)
+    gemm(a, w, epi=L.EPI_BF16, bias=bias, act=act, out=out, ldo=out.stride(0), block_n=block_n)
+    return out
+
+
+def linear_resid(a, w, bias, gamma, x, row_index=None, block_n=0):
+    """x(fp32)[row] += gamma * (a @ w^T + bias)."""
+    _chk(x, F32, "x")
+    gemm(a, w, epi=L.EPI_RESID, bias=bias, gamma=gamma, out=x, ldo=x.stride(0), row_index=row_index, block_n=block_n)
+    return x
+
+
+def rope_tables(maxpos: int, device, base: float = 100.0):
+    """fp32 cos/sin [maxpos, 16] exactly as the reference builds them (layers/rope.py:103-114, head half = 32)."""
+    exponents = torch.arange(0, 32, 2, device=device).float() / 32
+    inv_freq = 1.0 / (base ** exponents)
+    ang = torch.arange(maxpos, device=device, dtype=inv_freq.dtype)[:, None] * inv_freq[None]
+    return ang.cos().contiguous(), ang.sin().contiguous()
+
+
+def qkv_proj(a, w, bias, qn_w, qn_b, kn_w, kn_b, q, k, v, *, ntok, T, nspecial, wp, rope_cos, rope_sin, block_n=0):
+    C = w.shape[1]
+    gemm(a, w, epi=L.EPI_QKV, bias=bias, q_out=q, k_out=k, v_out=v, C=C, ntok=ntok, T=T, nspecial=nspecial, wp=wp,
+         maxpos=rope_cos.shape[0], qn_w=qn_w, qn_b=qn_b, kn_w=kn_w, kn_b=kn_b, rope_cos=rope_cos, rope_sin=rope_sin,
+         qscale=(1.0 / math.sqrt(64.0)) * math.log2(math.e), block_n=block_n)
+
+
+def attention(q, k, v, out, batch: int, heads: int, n: int):
+    for t, nm in ((q, "q"), (k, "k"), (v, "v"), (out, "out")):
+        _chk(t, BF16, nm)
+        assert t.is_contiguous()
+    L.check(L.lib().ovg_attention(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), batch, heads, n, L.stream()))
+    return out
+
+
+def layernorm(x, out, w=None, b=None, eps=1e-5, rows=None, grp_out=0, grp_in=0, grp_off=0):
+    assert x.dtype in (F32, BF16) and out.dtype == BF16 and x.stride(-1) == 1 and out.stride(-1) == 1
+    x2 = x if x.dim() == 2 else x.reshape(-1, x.shape[-1])
+    o2 = out if out.dim() == 2 else out.reshape(-1, out.shape[-1])
+    rows = o2.shape[0] if rows is None else rows
+    L.check(L.lib().ovg_layernorm(x2.data_ptr(), int(x.dtype == BF16), x2.stride(0), o2.data_ptr(), o2.stride(0), rows,
+                                  o2.shape[1], L.ptr(w), L.ptr(b), eps, grp_out, grp_in, grp_off, L.stream()))
+    return out
+
+
+def assemble_tokens(x, patch, cam_tok, reg_tok, inj0, placeholder, has_depth, K, S, T, R, C):
+    L.check(L.lib().ovg_assemble_tokens(x.data_ptr(), patch.data_ptr(), cam_tok.data_ptr(), reg_tok.data_ptr(),
+                                        inj0.data_ptr(), placeholder.data_ptr(), has_depth.data_ptr(), K, S, T, R, C,
+                                        L.stream()))
+
+
+def inject_snapshot(x, inj, slot, cam_out, K, T, C, coff):
+    L.check(L.lib().ovg_inject_snapshot(x.data_ptr(), L.ptr(inj), L.ptr(slot), L.ptr(cam_out), K, T, C, coff,
+                                        L.stream()))
+
+
+def depth_im2col(depth, mask, idx, scratch, cols, B, S, Sd, H, W, patch):
+    L.check(L.lib().ovg_depth_im2col(depth.data_ptr(), mask.data_ptr(), idx.data_ptr(), scratch.data_ptr(),
+                                     cols.data_ptr(), cols.stride(0), B, S, Sd, H, W, patch, L.stream()))
+
+
+def im2col3x3s2(src, dst, F, h, w, C):
+    L.check(L.lib().ovg_im2col3x3s2(src.data_ptr(), dst.data_ptr(), F, h, w, C, L.stream()))
+
+
+def upsample_bilinear(src, dst, table, F, h, w, H, W, C):
+    L.check(L.lib().ovg_upsample_bilinear(src.data_ptr(), dst.data_ptr(), L.ptr(table), F, h, w, H, W, C, L.stream()))

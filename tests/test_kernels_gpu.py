@@ -1,0 +1,323 @@
+"""Kernel-level parity (GPU): every libovg entry point against a plain PyTorch fp32 reference of the same op, through
+the C ABI.  Tolerances (stated per test) are for bf16 operands / fp32 accumulation."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+BF16, F32 = torch.bfloat16, torch.float32
+
+
+def _ops():
+    from omnivggt_official_b200 import ops
+    return ops
+
+
+def rel(a, b):
+    a, b = a.float(), b.float()
+    return ((a - b).norm() / b.norm().clamp(min=1e-12)).item()
+
+
+def randn(*s, scale=1.0, seed=0, dtype=F32):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return (torch.randn(*s, generator=g, device="cuda") * scale).to(dtype)
+
+
+# ----------------------------------------------------------------------------------------------- GEMM
+@pytest.mark.parametrize("M,N,K,bn", [(128, 64, 64, 0), (300, 256, 128, 0), (1000, 384, 192, 128), (2748, 3072, 1024, 256),
+                                      (515, 1024, 4096, 128), (77, 96, 392, 64)])
+def test_gemm_bf16_bias_gelu(M, N, K, bn):
+    ops = _ops()
+    a = randn(M, K, seed=1, dtype=BF16)
+    w = randn(N, K, scale=K ** -0.5, seed=2, dtype=BF16)
+    bias = randn(N, seed=3)
+    out = ops.linear_bf16(a, w, bias, act=ops.L.ACT_GELU, block_n=bn)
+    ref = F.gelu(a.float() @ w.float().t() + bias)
+    torch.cuda.synchronize()
+    assert rel(out, ref) < 6e-3          # bf16 output rounding ~ 2^-9
+    out2 = ops.linear_bf16(a, w, None, act=ops.L.ACT_NONE, block_n=bn)
+    assert rel(out2, a.float() @ w.float().t()) < 6e-3
+
+
+def test_gemm_resid_rowindex():
+    ops = _ops()
+    M, N, K = 1374 * 2, 1024, 1024
+    a = randn(M, K, seed=1, dtype=BF16)
+    w = randn(N, K, scale=K ** -0.5, seed=2, dtype=BF16)
+    bias, gamma = randn(N, seed=3), randn(N, seed=4)
+    x0 = randn(M, N, seed=5)
+    x = x0.clone()
+    ops.linear_resid(a, w, bias, gamma, x)
+    ref = x0 + gamma * (a.float() @ w.float().t() + bias)
+    assert rel(x, ref) < 1e-5 + 2e-3 * 0  # fp32 output: only accumulation-order noise
+    # scatter rows
+    perm = torch.randperm(M, device="cuda", dtype=torch.int32)
+    x = x0.clone()
+    ops.linear_resid(a, w, bias, gamma, x, row_index=perm)
+    ref2 = x0.clone()
+    ref2[perm.long()] += gamma * (a.float() @ w.float().t() + bias)
+    assert rel(x, ref2) < 1e-5
+
+
+def _rope_ref(t, pos, base=100.0):
+    # t [Bx,H,N,64] fp32, pos [Bx,N,2]
+    half = 32
+    inv = 1.0 / (base ** (torch.arange(0, half, 2, device=t.device).float() / half))
+
+    def one(z, p):
+        ang = p[:, None, :, None].float() * inv
+        c, s = ang.cos(), ang.sin()
+        a, b = z[..., :16], z[..., 16:]
+        return torch.cat([a * c - b * s, b * c + a * s], -1)
+
+    return torch.cat([one(t[..., :32], pos[..., 0]), one(t[..., 32:], pos[..., 1])], -1)
+
+
+@pytest.mark.parametrize("C,frames,hp,wp,S", [(128, 3, 4, 4, 3), (1024, 2, 37, 37, 2), (256, 4, 3, 5, 2)])
+def test_gemm_qkv_epilogue(C, frames, hp, wp, S):
+    """QKV linear + q/k LayerNorm(64) + 2-D RoPE + head-major layout vs reference formulas
+    (layers/attention.py:52-58, layers/rope.py:154-188)."""
+    ops = _ops()
+    heads, T = C // 64, hp * wp + 5
+    M = frames * T
+    a = randn(M, C, seed=1, dtype=BF16)
+    w = randn(3 * C, C, scale=C ** -0.5, seed=2, dtype=BF16)
+    bias = randn(3 * C, scale=0.1, seed=3)
+    qn_w, qn_b, kn_w, kn_b = 1 + 0.1 * randn(64, seed=4), 0.1 * randn(64, seed=5), 1 + 0.1 * randn(64, seed=6), 0.1 * randn(64, seed=7)
+    cos, sin = ops.rope_tables(max(hp, wp) + 1, "cuda")
+    for ntok in (T, S * T):   # frame-wise and global views of the same rows
+        if M % ntok:
+            continue
+        nb = M // ntok
+        q = torch.zeros(nb, heads, ntok, 64, device="cuda", dtype=BF16)
+        k, v = torch.zeros_like(q), torch.zeros_like(q)
+        ops.qkv_proj(a, w, bias, qn_w, qn_b, kn_w, kn_b, q, k, v, ntok=ntok, T=T, nspecial=5, wp=wp, rope_cos=cos, rope_sin=sin)
+        qkv = (a.float() @ w.float().t() + bias).reshape(nb, ntok, 3, heads, 64).permute(2, 0, 3, 1, 4)
+        yy, xx = torch.meshgrid(torch.arange(hp, device="cuda"), torch.arange(wp, device="cuda"), indexing="ij")
+        pos = torch.cat([torch.zeros(5, 2, device="cuda", dtype=torch.long), torch.stack([yy.reshape(-1), xx.reshape(-1)], -1) + 1])
+        pos = pos[None].expand(frames, -1, -1).reshape(nb, ntok, 2)
+        qr = _rope_ref(F.layer_norm(qkv[0], (64,), qn_w, qn_b, 1e-5), pos) * (math.log2(math.e) / 8.0)
+        kr = _rope_ref(F.layer_norm(qkv[1], (64,), kn_w, kn_b, 1e-5), pos)
+        torch.cuda.synchronize()
+        assert rel(q, qr) < 6e-3 and rel(k, kr) < 6e-3 and rel(v, qkv[2]) < 6e-3
+
+
+# ----------------------------------------------------------------------------------------------- attention
+@pytest.mark.parametrize("batch,heads,n", [(1, 1, 128), (1, 2, 256), (2, 2, 200), (3, 2, 1374), (1, 16, 2 * 1374), (1, 4, 700)])
+def test_attention(batch, heads, n):
+    """vs softmax(q k^T / 8) v in fp32 (layers/attention.py:61-66).  bf16 P and bf16 output: rel-L2 < 1e-2."""
+    ops = _ops()
+    q = randn(batch, heads, n, 64, seed=1)
+    k = randn(batch, heads, n, 64, seed=2)
+    v = randn(batch, heads, n, 64, seed=3)
+    qs = (q * (math.log2(math.e) / 8.0)).to(BF16)
+    kb, vb = k.to(BF16), v.to(BF16)
+    out = torch.zeros(batch, n, heads * 64, device="cuda", dtype=BF16)
+    ops.attention(qs, kb, vb, out, batch, heads, n)
+    s = (qs.float() * math.log(2.0)) @ kb.float().transpose(-1, -2)
+    ref = (s.softmax(-1) @ vb.float()).transpose(1, 2).reshape(batch, n, heads * 64)
+    torch.cuda.synchronize()
+    assert torch.isfinite(out.float()).all()
+    assert rel(out, ref) < 1e-2, rel(out, ref)
+
+
+def test_attention_peaky_rows_rescale():
+    """Large, growing logits force the lazy-rescale path (running max grows by > 8 between KV tiles)."""
+    ops = _ops()
+    batch, heads, n = 1, 2, 1024
+    q = randn(batch, heads, n, 64, seed=1)
+    k = randn(batch, heads, n, 64, seed=2) * torch.linspace(0.2, 6.0, n, device="cuda")[None, None, :, None]
+    v = randn(batch, heads, n, 64, seed=3)
+    qs, kb, vb = q.to(BF16), k.to(BF16), v.to(BF16)
+    out = torch.zeros(batch, n, heads * 64, device="cuda", dtype=BF16)
+    ops.attention(qs, kb, vb, out, batch, heads, n)
+    s = (qs.float() * math.log(2.0)) @ kb.float().transpose(-1, -2)
+    ref = (s.softmax(-1) @ vb.float()).transpose(1, 2).reshape(batch, n, heads * 64)
+    torch.cuda.synchronize()
+    assert torch.isfinite(out.float()).all()
+    assert rel(out, ref) < 1.5e-2, rel(out, ref)
+
+
+# ----------------------------------------------------------------------------------------------- LayerNorm & co
+@pytest.mark.parametrize("C", [128, 256, 1024, 2048])
+def test_layernorm(C):
+    ops = _ops()
+    x = randn(777, C, seed=1) * 3 + 0.5
+    w, b = 1 + 0.1 * randn(C, seed=2), 0.1 * randn(C, seed=3)
+    out = torch.empty(777, C, device="cuda", dtype=BF16)
+    ops.layernorm(x, out, w, b, 1e-5)
+    assert rel(out, F.layer_norm(x, (C,), w, b, 1e-5)) < 4e-3
+    # bf16 input, no affine, row gather that drops 5 special tokens per frame
+    T, P = 21, 16
+    xb = randn(4 * T, C, seed=4, dtype=BF16)
+    out2 = torch.empty(4 * P, C, device="cuda", dtype=BF16)
+    ops.layernorm(xb, out2, None, None, 1e-5, grp_out=P, grp_in=T, grp_off=5)
+    ref = F.layer_norm(xb.float().reshape(4, T, C)[:, 5:], (C,), None, None, 1e-5).reshape(4 * P, C)
+    assert rel(out2, ref) < 4e-3
+
+
+def test_assemble_and_inject():
+    ops = _ops()
+    B, S, P, R, C = 2, 3, 16, 4, 128
+    K, T = B * S, P + R + 1
+    patch, cam, reg = randn(K, P, C, seed=1), randn(2, C, seed=2), randn(2, R, C, seed=3)
+    inj0, ph = randn(K, C, seed=4), randn(C, seed=5)
+    has = torch.tensor([1, 0, 0, 1, 1, 0], device="cuda", dtype=torch.int32)
+    x = torch.empty(K, T, C, device="cuda")
+    ops.assemble_tokens(x, patch, cam, reg, inj0, ph, has, K, S, T, R, C)
+    slot = torch.tensor([0, 1, 1, 0, 1, 1], device="cuda")
+    ref = torch.cat([(cam[slot] + inj0)[:, None], reg[slot], patch + (1 - has.float())[:, None, None] * ph], 1)
+    assert torch.equal(x, ref)
+    inj = randn(K, C, seed=6)
+    slotbuf = torch.zeros(K * T, 2 * C, device="cuda", dtype=BF16)
+    camout = torch.zeros(K, 2 * C, device="cuda")
+    ops.inject_snapshot(x, inj, slotbuf, camout, K, T, C, C)
+    ref[:, 0] += inj
+    assert torch.equal(x, ref)
+    assert torch.equal(slotbuf[:, C:], ref.reshape(K * T, C).to(BF16)) and (slotbuf[:, :C] == 0).all()
+    assert torch.equal(camout[:, C:], ref[:, 0])
+
+
+def test_depth_im2col_matches_reference_normalisation():
+    ops = _ops()
+    B, S, H, W, patch = 2, 4, 28, 42, 14
+    idx = torch.tensor([0, 2, 3], device="cuda", dtype=torch.int32)
+    depth = 0.5 + 4 * torch.rand(B, S, H, W, device="cuda")
+    mask = (torch.rand(B, S, H, W, device="cuda") > 0.3).float()
+    mask[1] = 0          # scene without valid pixels -> zeros (omnivggt_aggregator.py:121-122)
+    Sd, hp, wp = 3, H // patch, W // patch
+    cols = torch.zeros(B * Sd * hp * wp, 2 * patch * patch, device="cuda", dtype=BF16)
+    scratch = torch.zeros(B * 128 * 2, device="cuda", dtype=torch.float64)
+    ops.depth_im2col(depth, mask, idx, scratch, cols, B, S, Sd, H, W, patch)
+    d, m = depth[:, idx.long()], mask[:, idx.long()]
+    norm = torch.zeros_like(d)
+    for b in range(B):
+        valid = d[b][m[b] > 0]
+        if valid.numel():
+            norm[b] = d[b] / (valid.mean() + 1e-8) * m[b]
+    dm = torch.stack([norm.reshape(-1, H, W), m.reshape(-1, H, W)], 1)
+    ref = F.unfold(dm, kernel_size=patch, stride=patch).transpose(1, 2).reshape(-1, 2 * patch * patch)
+    assert rel(cols, ref) < 4e-3
+
+
+# ----------------------------------------------------------------------------------------------- conv family
+def _to_pad(x):  # NCHW fp32 -> zero-bordered NHWC bf16 [F,h+2,w+2,C]
+    return F.pad(x.permute(0, 2, 3, 1), (0, 0, 1, 1, 1, 1)).to(BF16).contiguous()
+
+
+def _from_pad(p):  # -> NCHW fp32 interior
+    return p[:, 1:-1, 1:-1].float().permute(0, 3, 1, 2)
+
+
+@pytest.mark.parametrize("Fr,h,w,Cin,Cout", [(2, 9, 7, 64, 64), (1, 37, 37, 256, 256), (2, 19, 19, 128, 32)])
+def test_conv3x3_taps_with_skips_relu(Fr, h, w, Cin, Cout):
+    """3x3 conv as 9 row-shifted GEMMs over the zero-bordered layout + bias + two skips + ReLU
+    (heads/dpt_head.py:379-399)."""
+    ops = _ops()
+    x = randn(Fr, Cin, h, w, seed=1)
+    wt = randn(Cout, Cin, 3, 3, scale=(9 * Cin) ** -0.5, seed=2)
+    bias = randn(Cout, seed=3)
+    s1, s2 = randn(Fr, Cout, h, w, seed=4), randn(Fr, Cout, h, w, seed=5)
+    xp, s1p, s2p = _to_pad(x), _to_pad(s1), _to_pad(s2)
+    wb = wt.permute(0, 2, 3, 1).reshape(Cout, 9 * Cin).to(BF16).contiguous()
+    outp = torch.full((Fr, h + 2, w + 2, Cout), 7.0, device="cuda", dtype=BF16)
+    taps = [(ky - 1) * (w + 2) + (kx - 1) for ky in range(3) for kx in range(3)]
+    ops.gemm(xp.reshape(-1, Cin), wb, taps=taps, epi=ops.L.EPI_BF16, bias=bias, act=ops.L.ACT_RELU, out=outp,
+             ldo=Cout, skip1=s1p, skip2=s2p, rowmap=ops.L.ROWS_PAD, gh=h, gw=w)
+    ref = F.relu(F.conv2d(xp[:, 1:-1, 1:-1].float().permute(0, 3, 1, 2), wb.float().reshape(Cout, 3, 3, Cin).permute(0, 3, 1, 2),
+                          bias, padding=1) + s1p[:, 1:-1, 1:-1].float().permute(0, 3, 1, 2) + s2p[:, 1:-1, 1:-1].float().permute(0, 3, 1, 2))
+    torch.cuda.synchronize()
+    assert rel(_from_pad(outp), ref) < 6e-3
+    border = outp.clone()
+    border[:, 1:-1, 1:-1] = 0
+    assert (border == 0).all()         # border rows are rewritten as zeros
+
+
+@pytest.mark.parametrize("ps,Cin,Cout,h,w", [(4, 64, 64, 5, 3), (2, 128, 128, 4, 4), (4, 256, 256, 37, 37)])
+def test_conv_transpose_pixel_shuffle(ps, Cin, Cout, h, w):
+    """ConvTranspose2d(k = s) as one GEMM with a pixel-shuffle store (heads/dpt_head.py:84-89)."""
+    ops = _ops()
+    Fr = 2
+    x = randn(Fr, Cin, h, w, seed=1)
+    wt = randn(Cin, Cout, ps, ps, scale=Cin ** -0.5, seed=2)
+    bias = randn(Cout, seed=3)
+    a = x.permute(0, 2, 3, 1).reshape(-1, Cin).to(BF16).contiguous()
+    wb = wt.permute(2, 3, 1, 0).reshape(ps * ps * Cout, Cin).to(BF16).contiguous()
+    outp = torch.zeros(Fr, h * ps + 2, w * ps + 2, Cout, device="cuda", dtype=BF16)
+    ops.gemm(a, wb, epi=ops.L.EPI_BF16, bias=bias, out=outp, ldo=Cout, rowmap=ops.L.ROWS_PIXSHUF, gh=h, gw=w, ps=ps, cout=Cout)
+    ref = F.conv_transpose2d(a.float().reshape(Fr, h, w, Cin).permute(0, 3, 1, 2), wb.float().reshape(ps, ps, Cout, Cin).permute(3, 2, 0, 1),
+                             bias, stride=ps)
+    torch.cuda.synchronize()
+    assert rel(_from_pad(outp), ref) < 6e-3
+
+
+def test_dense2pad_with_table():
+    ops = _ops()
+    Fr, h, w, Cin, Cout = 3, 5, 7, 256, 128
+    a = randn(Fr * h * w, Cin, seed=1, dtype=BF16)
+    wb = randn(Cout, Cin, scale=Cin ** -0.5, seed=2, dtype=BF16)
+    bias, table = randn(Cout, seed=3), randn(h * w, Cout, seed=4)
+    outp = torch.zeros(Fr, h + 2, w + 2, Cout, device="cuda", dtype=BF16)
+    ops.gemm(a, wb, epi=ops.L.EPI_BF16, bias=bias, table=table, table_rows=h * w, out=outp, ldo=Cout,
+             rowmap=ops.L.ROWS_DENSE2PAD, gh=h, gw=w)
+    ref = (a.float() @ wb.float().t() + bias).reshape(Fr, h * w, Cout) + table
+    assert rel(outp[:, 1:-1, 1:-1].reshape(Fr, h * w, Cout), ref) < 6e-3
+
+
+def test_im2col_s2_and_conv():
+    ops = _ops()
+    Fr, h, w, C, Cout = 2, 7, 5, 64, 64
+    x = randn(Fr, C, h, w, seed=1)
+    wt = randn(Cout, C, 3, 3, scale=(9 * C) ** -0.5, seed=2)
+    src = x.permute(0, 2, 3, 1).to(BF16).contiguous()
+    oh, ow = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+    cols = torch.empty(Fr * oh * ow, 9 * C, device="cuda", dtype=BF16)
+    ops.im2col3x3s2(src, cols, Fr, h, w, C)
+    wb = wt.permute(0, 2, 3, 1).reshape(Cout, 9 * C).to(BF16).contiguous()
+    out = ops.linear_bf16(cols, wb)
+    ref = F.conv2d(src.float().permute(0, 3, 1, 2), wb.float().reshape(Cout, 3, 3, C).permute(0, 3, 1, 2), None, stride=2, padding=1)
+    assert rel(out.float().reshape(Fr, oh, ow, Cout).permute(0, 3, 1, 2), ref) < 6e-3
+
+
+@pytest.mark.parametrize("h,w,H,W,C", [(4, 4, 8, 8, 64), (19, 19, 37, 37, 256), (8, 12, 14, 21, 128), (1, 1, 3, 3, 64)])
+def test_upsample_bilinear(h, w, H, W, C):
+    ops = _ops()
+    Fr = 2
+    x = randn(Fr, C, h, w, seed=1)
+    table = randn(H * W, C, seed=2)
+    xp = _to_pad(x)
+    dst = torch.full((Fr, H + 2, W + 2, C), 3.0, device="cuda", dtype=BF16)
+    ops.upsample_bilinear(xp, dst, table, Fr, h, w, H, W, C)
+    ref = F.interpolate(xp[:, 1:-1, 1:-1].float().permute(0, 3, 1, 2), size=(H, W), mode="bilinear", align_corners=True)
+    ref = ref + table.reshape(H, W, C).permute(2, 0, 1)
+    assert rel(_from_pad(dst), ref) < 5e-3
+    b = dst.clone()
+    b[:, 1:-1, 1:-1] = 0
+    assert (b == 0).all()
+
+
+@pytest.mark.parametrize("outc,act", [(2, 0), (4, 1)])
+def test_head_tail(outc, act):
+    """3x3 conv 128->32 + ReLU + 1x1 32->outc + activations (heads/dpt_head.py:121-126; heads/head_act.py:61-125)."""
+    ops = _ops()
+    Fr, h, w, Cin = 2, 14, 28, 128
+    x = randn(Fr, Cin, h, w, seed=1)
+    w1 = randn(32, Cin, 3, 3, scale=(9 * Cin) ** -0.5, seed=2)
+    b1 = randn(32, scale=0.1, seed=3)
+    w2 = randn(outc, 32, scale=32 ** -0.5, seed=4)
+    b2 = randn(outc, scale=0.1, seed=5)
+    xp = _to_pad(x)
+    wb = w1.permute(0, 2, 3, 1).reshape(32, 9 * Cin).to(BF16).contiguous()
+    preds = torch.zeros(Fr, h, w, outc - 1, device="cuda")
+    conf = torch.zeros(Fr, h, w, device="cuda")
+    taps = [(ky - 1) * (w + 2) + (kx - 1) for ky in range(3) for kx in range(3)]
+    ops.gemm(xp.reshape(-1, Cin), wb, taps=taps, epi=ops.L.EPI_HEADTAIL, bias=b1, w2=w2.contiguous(), b2=b2, outc=outc,
+             head_act=act, preds=preds, conf=conf, rowmap=ops.L.ROWS_PAD, gh=h, gw=w)
+    y = F.conv2d(xp[:, 1:-1, 1:-1].float().permute(0, 3, 1, 2), wb.float().reshape(32, 3, 3, Cin).permute(0, 3, 1, 2), b1, padding=1)
+    y = F.conv2d(F.relu(y), w2[:, :, None, None], b2).permute(0, 2, 3, 1)
+    pr = torch.exp(y[..., :-1]) if act == 0 else torch.sign(y[..., :-1]) * torch.expm1(y[..., :-1].abs())
+    torch.cuda.synchronize()
+    assert rel(preds, pr) < 1e-2 and rel(conf, 1 + y[..., -1].exp()) < 1e-2

@@ -1,0 +1,81 @@
+"""Kernel micro-benchmarks at the cfg2 shapes (B=1, S=8, 518^2): CUDA-event timing, L2 flushed between iterations."""
+import json
+import math
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from omnivggt_official_b200 import ops  # noqa: E402
+
+BF16 = torch.bfloat16
+dev = "cuda"
+flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+
+def timeit(fn, iters=10, warm=3):
+    for _ in range(warm):
+        fn()
+    ts = []
+    for _ in range(iters):
+        flush_buf.zero_()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        fn()
+        e.record()
+        torch.cuda.synchronize()
+        ts.append(s.elapsed_time(e))
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+res = {}
+S, T, C = int(os.environ.get("S", 8)), 1374, 1024
+M = S * T
+a = torch.randn(M, C, device=dev).to(BF16)
+for name, N, K, bns in (("qkv", 3072, 1024, (128, 256)), ("proj", 1024, 1024, (128, 256)), ("fc1", 4096, 1024, (128, 256)), ("fc2", 1024, 4096, (128, 256))):
+    x = torch.randn(M, K, device=dev).to(BF16)
+    w = (torch.randn(N, K, device=dev) * K ** -0.5).to(BF16)
+    bias = torch.randn(N, device=dev)
+    out = torch.empty(M, N, device=dev, dtype=BF16)
+    xres = torch.randn(M, N, device=dev)
+    gamma = torch.randn(N, device=dev)
+    for bn in bns:
+        if name in ("proj", "fc2"):
+            ms = timeit(lambda: ops.linear_resid(x, w, bias, gamma, xres, block_n=bn))
+        elif name == "fc1":
+            ms = timeit(lambda: ops.linear_bf16(x, w, bias, act=ops.L.ACT_GELU, out=out, block_n=bn))
+        else:
+            ms = timeit(lambda: ops.linear_bf16(x, w, bias, out=out, block_n=bn))
+        res[f"gemm_{name}_bn{bn}"] = dict(ms=ms, tflops=2 * M * N * K / ms / 1e9)
+    ms = timeit(lambda: torch.matmul(x, w.t()))
+    res[f"cublas_{name}"] = dict(ms=ms, tflops=2 * M * N * K / ms / 1e9)
+# qkv epilogue
+w = (torch.randn(3 * C, C, device=dev) * C ** -0.5).to(BF16)
+bias = torch.randn(3 * C, device=dev)
+ones, zeros = torch.ones(64, device=dev), torch.zeros(64, device=dev)
+cos, sin = ops.rope_tables(38, dev)
+q = torch.empty(1, 16, M, 64, device=dev, dtype=BF16)
+k, v = torch.empty_like(q), torch.empty_like(q)
+ms = timeit(lambda: ops.qkv_proj(a, w, bias, ones, zeros, ones, zeros, q, k, v, ntok=M, T=T, nspecial=5, wp=37, rope_cos=cos, rope_sin=sin))
+res["gemm_qkv_fused"] = dict(ms=ms, tflops=2 * M * 3 * C * C / ms / 1e9)
+# attention: global and frame
+o = torch.empty(1, M, C, device=dev, dtype=BF16)
+ms = timeit(lambda: ops.attention(q, k, v, o, 1, 16, M), iters=5)
+res["attn_global"] = dict(ms=ms, tflops=4 * M * M * C / ms / 1e9)
+qf, kf, vf = (t.reshape(16, S, T, 64).transpose(0, 1).contiguous() for t in (q, k, v))
+ms = timeit(lambda: ops.attention(qf, kf, vf, o, S, 16, T))
+res["attn_frame"] = dict(ms=ms, tflops=4 * S * T * T * C / ms / 1e9)
+import torch.nn.functional as F
+ms = timeit(lambda: F.scaled_dot_product_attention(q, k, v), iters=5)
+res["sdpa_global_torch"] = dict(ms=ms, tflops=4 * M * M * C / ms / 1e9)
+# layernorm
+x32 = torch.randn(M, C, device=dev)
+ln_out = torch.empty(M, C, device=dev, dtype=BF16)
+ms = timeit(lambda: ops.layernorm(x32, ln_out, torch.ones(C, device=dev), torch.zeros(C, device=dev)))
+res["layernorm"] = dict(ms=ms, gbs=M * C * 6 / ms / 1e6)
+for k_, v_ in res.items():
+    print(k_, json.dumps(v_))
+os.makedirs("gpurun_out", exist_ok=True)
+json.dump(res, open("gpurun_out/kbench.json", "w"), indent=1)
