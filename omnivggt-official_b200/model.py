@@ -1,0 +1,137 @@
+"""Drop-in ``OmniVGGT`` module: the reference's constructor / forward / state-dict contract
+(reference omnivggt/models/omnivggt.py:10-68, consumed by inference.py:321-356) on the B200-native engine.
+
+    model = OmniVGGT().to("cuda").eval()
+    model.load_state_dict(load_file("checkpoints/OmniVGGT.safetensors"))     # strict, same 1 505 keys
+    predictions = model(images=..., extrinsics=..., intrinsics=..., depth=..., mask=...,
+                        depth_gt_index=[...], camera_gt_index=[...])
+
+Differences from the reference are additive only: aux tensors / index lists may be None, no network access at
+construction, and extra keyword arguments select reduced architectures for tests.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence
+
+import torch
+import torch.nn as nn
+
+try:  # keep from_pretrained / save_pretrained like the reference (omnivggt.py:3,:10)
+    from huggingface_hub import PyTorchModelHubMixin
+except Exception:  # pragma: no cover
+    class PyTorchModelHubMixin:  # type: ignore
+        pass
+
+from . import torch_parts as TP
+from .params import AggregatorParams, CameraHeadParams, DPTParams, init_parameters
+
+_RESNET_MEAN = (0.485, 0.456, 0.406)   # reference models/aggregator.py:22-23
+_RESNET_STD = (0.229, 0.224, 0.225)
+
+
+class OmniVGGT(nn.Module, PyTorchModelHubMixin):
+    def __init__(self, img_size: int = 518, patch_size: int = 14, embed_dim: int = 1024, *, depth: int = 24,
+                 patch_embed: str = "dinov2_vitl14_reg", dino_depth: int = 24, dino_heads: int = 16,
+                 num_register_tokens: int = 4, dpt_features: int = 256,
+                 dpt_out_channels: Sequence[int] = (256, 512, 1024, 1024),
+                 dpt_layers: Sequence[int] = (4, 11, 17, 23), camera_heads: int = 16, camera_trunk_depth: int = 4,
+                 dino_dtype: torch.dtype = torch.bfloat16, init_seed: Optional[int] = 0):
+        super().__init__()
+        self.img_size, self.patch_size, self.embed_dim = img_size, patch_size, embed_dim
+        self.dpt_layers = tuple(dpt_layers)
+        self.dino_dtype = dino_dtype
+        pe = "conv" if "conv" in patch_embed else "dino"
+        self.aggregator = AggregatorParams(img_size, patch_size, embed_dim, depth, 64, num_register_tokens, pe,
+                                           dino_depth, dino_heads)
+        self.camera_head = CameraHeadParams(2 * embed_dim, camera_trunk_depth, camera_heads)
+        self.point_head = DPTParams(2 * embed_dim, 4, dpt_features, list(dpt_out_channels))   # inv_log / expp1
+        self.depth_head = DPTParams(2 * embed_dim, 2, dpt_features, list(dpt_out_channels))   # exp / expp1
+        self.register_buffer("_resnet_mean", torch.tensor(_RESNET_MEAN).view(1, 1, 3, 1, 1), persistent=False)
+        self.register_buffer("_resnet_std", torch.tensor(_RESNET_STD).view(1, 1, 3, 1, 1), persistent=False)
+        if init_seed is not None:
+            init_parameters(self, init_seed, dezero=False)
+        self._engine = None
+
+    # ---------------------------------------------------------------------------------------------- packing
+    def randomize_(self, seed: int = 0, dezero: bool = True) -> "OmniVGGT":
+        """Synthetic weights on the current device (benchmarks / smoke test; there is no checkpoint offline)."""
+        init_parameters(self, seed, dezero)
+        self._engine = None
+        return self
+
+    def _load_from_state_dict(self, *a, **k):  # invalidate packed weights on any (re)load
+        self._engine = None
+        return super()._load_from_state_dict(*a, **k)
+
+    def load_state_dict(self, *a, **k):
+        self._engine = None
+        return super().load_state_dict(*a, **k)
+
+    def _apply(self, fn, *a, **k):
+        self._engine = None
+        return super()._apply(fn, *a, **k)
+
+    def engine(self):
+        """Repack weights into kernel layouts (bf16, K-major, folded LayerNorm affines) on first use."""
+        if self._engine is None:
+            from .engine import Engine          # imports the CUDA library; fails loudly if it is missing
+            if next(self.parameters()).device.type != "cuda":
+                raise RuntimeError("OmniVGGT (B200 engine) has no CPU path: move the module to a CUDA device")
+            self._engine = Engine(self)
+        return self._engine
+
+    # ---------------------------------------------------------------------------------------------- forward
+    @torch.no_grad()
+    def forward(self, images: torch.Tensor, extrinsics: torch.Tensor = None, intrinsics: torch.Tensor = None,
+                depth: torch.Tensor = None, mask: torch.Tensor = None, depth_gt_index: list = None,
+                camera_gt_index: list = None) -> Dict[str, object]:
+        if images.dim() == 4:
+            images = images.unsqueeze(0)
+        B, S, Cin, H, W = images.shape
+        if Cin != 3:
+            raise ValueError(f"Expected 3 input channels, got {Cin}")                 # omnivggt_aggregator.py:139-140
+        assert H % self.patch_size == 0, f"Input image height {H} is not a multiple of patch height {self.patch_size}"
+        assert W % self.patch_size == 0, f"Input image width {W} is not a multiple of patch width: {self.patch_size}"
+        depth_idx = list(depth_gt_index) if depth_gt_index is not None else []
+        cam_idx = list(camera_gt_index) if camera_gt_index is not None else []
+        if len(depth_idx):
+            assert depth is not None and mask is not None, "depth_gt_index given without depth / mask"
+            assert tuple(depth.shape[:4]) == tuple(mask.shape), "mask and depth must have the same first four dimensions"
+        if len(cam_idx):
+            assert extrinsics is not None and intrinsics is not None, "camera_gt_index given without cameras"
+        eng = self.engine()
+        ag = self.aggregator
+        K = B * S
+
+        # ---- frozen patchifier (PyTorch): normalise, DINOv2 / conv patch embed       (omnivggt_aggregator.py:143-150)
+        img = ((images.float() - self._resnet_mean) / self._resnet_std).view(K, Cin, H, W)
+        if hasattr(ag.patch_embed, "blocks"):
+            patch = TP.dino_patchify(ag.patch_embed, img, self.patch_size, self.dino_dtype)
+        else:
+            pe = ag.patch_embed.proj
+            patch = torch.nn.functional.conv2d(img, pe.weight, pe.bias, stride=self.patch_size).flatten(2).transpose(1, 2)
+        patch = patch.float().contiguous()
+
+        # ---- aux cameras -> pose encoding -> 25 injection vectors (tiny fp32 host math)  (:158-182,:273-287)
+        pose = None
+        if len(cam_idx):
+            ci = torch.tensor(cam_idx, device=images.device)
+            pose = TP.aux_pose_encoding(extrinsics.index_select(1, ci), intrinsics.index_select(1, ci), H, W)
+        inj = TP.injection_vectors(ag, pose, cam_idx, B, S)
+
+        # ---- hot path: aggregator on libovg
+        keep = set(self.dpt_layers)
+        slots, cam_tokens = eng.aggregate(patch, inj, depth, mask, depth_idx, B, S, H, W, keep)
+
+        predictions: Dict[str, object] = {}
+        pose_list = TP.camera_head(self.camera_head, cam_tokens.view(B, S, -1))
+        predictions["pose_enc"] = pose_list[-1]
+        predictions["pose_enc_list"] = pose_list
+        d, dc = eng.dpt("depth_head", slots, self.dpt_layers, K, H, W, head_act=0)
+        predictions["depth"] = d.view(B, S, H, W, 1)
+        predictions["depth_conf"] = dc.view(B, S, H, W)
+        p, pc = eng.dpt("point_head", slots, self.dpt_layers, K, H, W, head_act=1)
+        predictions["world_points"] = p.view(B, S, H, W, 3)
+        predictions["world_points_conf"] = pc.view(B, S, H, W)
+        predictions["images"] = images
+        return predictions
