@@ -131,6 +131,7 @@ class Engine:
         self.dpt = {name: DPTPack(getattr(model, name)) for name in ("depth_head", "point_head")
                     if getattr(model, name, None) is not None}
         self.ws = Workspace(self.device)
+        self.attn_events = None      # bench.py sets this to a list to time the global-attention launches
         self._rope: Dict[int, Tuple[torch.Tensor, torch.Tensor]] = {}
         self._tables: Dict[tuple, torch.Tensor] = {}
 
@@ -160,7 +161,14 @@ class Engine:
         ops.layernorm(x2, xn, bp.ln1_w, bp.ln1_b, 1e-5)
         ops.qkv_proj(xn, bp.w_qkv, bp.b_qkv, bp.qn_w, bp.qn_b, bp.kn_w, bp.kn_b, q, k, v, ntok=ntok, T=T,
                      nspecial=self.R + 1, wp=wp, rope_cos=rope[0], rope_sin=rope[1])
-        ops.attention(q, k, v, o, batch, self.heads, ntok)
+        if self.attn_events is not None and ntok > T:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            ops.attention(q, k, v, o, batch, self.heads, ntok)
+            e1.record()
+            self.attn_events.append((e0, e1, batch, ntok))
+        else:
+            ops.attention(q, k, v, o, batch, self.heads, ntok)
         ops.linear_resid(o, bp.w_proj, bp.b_proj, bp.g1, x2)
         ops.layernorm(x2, xn, bp.ln2_w, bp.ln2_b, 1e-5)
         ops.linear_bf16(xn, bp.w_fc1, bp.b_fc1, act=L.ACT_GELU, out=h)

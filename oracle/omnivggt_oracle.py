@@ -94,8 +94,7 @@ def attention(sd: SD, pre: str, x: Tensor, heads: int, pos: Optional[Tensor], qk
     if pos is not None:
         q = rope_2d(q, pos, rope_base)
         k = rope_2d(k, pos, rope_base)
-    s = (q * dh ** -0.5) @ k.transpose(-1, -2)
-    o = s.softmax(dim=-1) @ v
+    o = F.scaled_dot_product_attention(q, k, v)          # attention.py:61-66 (default scale dh^-0.5, no mask)
     o = o.transpose(1, 2).reshape(Bx, N, C)
     return linear(o, sd, pre + ".proj")
 

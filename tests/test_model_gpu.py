@@ -1,0 +1,128 @@
+"""Model-level parity (GPU): the drop-in OmniVGGT module (CUDA engine) against
+  (a) golden outputs of the unmodified reference (tests/golden, reduced configs, all index patterns), and
+  (b) the fp32 CPU oracle at full width (C = 1024, DINOv2 patchifier) on a reduced depth / image size,
+plus size-independent properties at the BASELINE image size.
+
+Tolerance.  The kernels compute with bf16 operands and fp32 accumulation (the reference runs fp32), so the bar is stated
+as relative L2 per output: 3e-2 on the reduced configs / full-width model (measured deviations are recorded in
+profiles/ and DESIGN.md); pose_enc additionally max-abs 5e-2."""
+import json
+import os
+
+import pytest
+import torch
+from safetensors.torch import load_file
+
+from conftest import GOLDEN, golden_index, golden_schema
+from oracle.synth import make_inputs, make_state_dict
+
+pytestmark = pytest.mark.gpu
+INDEX = golden_index()
+TOL = 3e-2
+KEYS = ("pose_enc", "depth", "depth_conf", "world_points", "world_points_conf")
+
+
+def rel(a, b):
+    a, b = a.float().cpu(), b.float().cpu()
+    return ((a - b).norm() / b.norm().clamp(min=1e-12)).item()
+
+
+def build(variant, dino_dtype=torch.float32):
+    from omnivggt_official_b200 import OmniVGGT
+    meta = golden_schema(variant)
+    v = meta["variant"]
+    kw = dict(img_size=v["img_size"], embed_dim=v["embed_dim"], depth=v["depth"], dpt_features=v["features"],
+              dpt_out_channels=v["out_channels"], dpt_layers=tuple(range(v["depth"]))[-4:], camera_heads=v["cam_heads"],
+              camera_trunk_depth=v["cam_trunk"], dino_dtype=dino_dtype)
+    kw.update(patch_embed="conv") if v["patch_embed"] == "conv" else kw.update(patch_embed="dino", dino_depth=2, dino_heads=2)
+    m = OmniVGGT(**kw)
+    m.load_state_dict(make_state_dict(meta["schema"], 0), strict=True)
+    return m.cuda().eval()
+
+
+_MODELS = {}
+
+
+def model(variant):
+    if variant not in _MODELS:
+        _MODELS[variant] = build(variant)
+    return _MODELS[variant]
+
+
+@pytest.mark.parametrize("case", sorted(INDEX))
+def test_matches_reference_golden(case):
+    meta = INDEX[case]
+    m = model(meta["variant"])
+    inp = {k: v.cuda() for k, v in make_inputs(meta["B"], meta["S"], meta["H"], meta["W"], seed=meta["input_seed"]).items()}
+    out = m(depth_gt_index=meta["depth_gt_index"], camera_gt_index=meta["camera_gt_index"], **inp)
+    torch.cuda.synchronize()
+    ref = load_file(os.path.join(GOLDEN, f"{case}.safetensors"))
+    errs = {k: rel(out[k], ref[k]) for k in KEYS}
+    print(case, json.dumps(errs))
+    for k in KEYS:
+        assert out[k].shape == ref[k].shape and out[k].dtype == torch.float32 and out[k].is_cuda
+        assert torch.isfinite(out[k]).all(), k
+        assert errs[k] < TOL, (k, errs)
+    assert (out["pose_enc"].cpu() - ref["pose_enc"]).abs().max() < 5e-2
+    assert len(out["pose_enc_list"]) == 4 and out["images"].shape == (meta["B"], meta["S"], 3, meta["H"], meta["W"])
+
+
+def test_api_quirks_and_errors():
+    m = model("mini_conv")
+    inp = {k: v.cuda() for k, v in make_inputs(1, 2, 56, 56, seed=11).items()}
+    a = m(images=inp["images"][0])                           # 4-D input gets a batch dim (omnivggt.py:31-32)
+    b = m(images=inp["images"], extrinsics=inp["extrinsics"], intrinsics=inp["intrinsics"], depth=torch.zeros_like(inp["depth"]),
+          mask=torch.zeros_like(inp["mask"]), depth_gt_index=[], camera_gt_index=[])      # what inference.py passes
+    assert torch.equal(a["depth"], b["depth"]) and a["images"].shape == (1, 2, 3, 56, 56)
+    with pytest.raises(ValueError):
+        m(images=torch.zeros(1, 2, 4, 56, 56, device="cuda"))
+    with pytest.raises(AssertionError):
+        m(images=torch.zeros(1, 2, 3, 50, 56, device="cuda"))
+
+
+def test_batch_independence_and_determinism():
+    """Scenes are independent (B is a pure batch dim): a scene's outputs do not depend on its batch neighbours, and a
+    repeated call is bit-identical (no atomics on the path)."""
+    m = model("mini_conv")
+    inp = {k: v.cuda() for k, v in make_inputs(2, 3, 56, 56, seed=12).items()}
+    both = m(depth_gt_index=[1], camera_gt_index=[0, 2], **inp)
+    again = m(depth_gt_index=[1], camera_gt_index=[0, 2], **inp)
+    one = m(depth_gt_index=[1], camera_gt_index=[0, 2], **{k: v[1:2] for k, v in inp.items()})
+    for k in KEYS:
+        assert torch.equal(both[k], again[k]), k
+        assert rel(both[k][1:2], one[k]) < 2e-3, (k, rel(both[k][1:2], one[k]))
+
+
+def test_view_permutation_equivariance():
+    """Views 1..S-1 are exchangeable (no cross-frame position code; only view 0 uses the first camera/register slot)."""
+    m = model("mini_conv")
+    inp = {k: v.cuda() for k, v in make_inputs(1, 4, 56, 56, seed=13).items()}
+    perm = [0, 3, 1, 2]
+    a = m(**inp, depth_gt_index=[], camera_gt_index=[])
+    b = m(**{k: v[:, perm] for k, v in inp.items()}, depth_gt_index=[], camera_gt_index=[])
+    for k in KEYS:
+        assert rel(b[k], a[k][:, perm]) < 1e-2, (k, rel(b[k], a[k][:, perm]))
+
+
+@pytest.mark.parametrize("aux", [False, True])
+def test_full_width_vs_oracle(aux):
+    """C = 1024 / 16 heads / DINOv2 ViT-L patchifier / DPT features 256 (the real widths) with depth 4 + 4 blocks and a
+    154 x 210 image so that the fp32 CPU oracle finishes in seconds."""
+    from omnivggt_official_b200 import OmniVGGT
+    from oracle.omnivggt_oracle import OracleConfig, omnivggt_forward
+    torch.manual_seed(0)
+    m = OmniVGGT(img_size=518, depth=4, dino_depth=2, dpt_layers=(0, 1, 2, 3), camera_trunk_depth=2, dino_dtype=torch.float32)
+    schema = {k: list(v.shape) for k, v in m.state_dict().items()}
+    sd = make_state_dict(schema, 0)
+    m.load_state_dict(sd)
+    m = m.cuda().eval()
+    B, S, H, W = 1, 3, 154, 210
+    inp = make_inputs(B, S, H, W, seed=21)
+    didx, cidx = ([0, 2], [0, 1]) if aux else ([], [])
+    out = m(depth_gt_index=didx, camera_gt_index=cidx, **{k: v.cuda() for k, v in inp.items()})
+    torch.cuda.synchronize()
+    ref = omnivggt_forward(sd, depth_gt_index=didx, camera_gt_index=cidx, cfg=OracleConfig(dpt_layers=(0, 1, 2, 3)), **inp)
+    errs = {k: rel(out[k], ref[k]) for k in KEYS}
+    print("full_width", aux, json.dumps(errs))
+    for k in KEYS:
+        assert errs[k] < TOL, errs
