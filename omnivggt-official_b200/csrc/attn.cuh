@@ -8,7 +8,8 @@
 //   warp 0        TMA producer: Q tiles once, K/V tiles through a 4-stage ring
 //   warp 1        MMA issuer:   S_t = Q_t K^T (SS, M128 N128 K64) and O_t += P_t V (TS: P read from TMEM,
 //                               V as MN-major smem operand, M128 N64 K128); issue order PV_t(j), S_t(j+1)
-//   warps 4-7     softmax for tile 0 (one query row per thread; row = TMEM lane)
+//   warps 4-7     softmax for tile 0 (one query row per thread; row = TMEM lane; the whole 128-wide S row is
+//                 held in registers: one TMEM read per element; setmaxnreg moves registers from warps 0-3 here)
 //   warps 8-11    softmax for tile 1
 // TMEM (512 cols): S0 [0,128) S1 [128,256) O0 [256,320) O1 [320,384); P_t (bf16x2) aliases S_t[0,64).
 // Online softmax with lazy rescaling: O/l are rescaled only when the running max grows by > 8 (log2 units),
@@ -30,6 +31,17 @@ constexpr int ATT_KV_STAGES = 4;
 constexpr int ATT_TILE_BYTES = 128 * 64 * 2;
 constexpr int ATT_SMEM_BYTES = 1024 + (2 + 2 * ATT_KV_STAGES) * ATT_TILE_BYTES + 512;
 
+template <int N>
+__device__ __forceinline__ void reg_alloc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void reg_dealloc() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {   // packed fp32x2 add (sm_100 FADD2)
+  float2 d;
+  asm("add.rn.f32x2 %0, %1, %2;"
+      : "=l"(reinterpret_cast<uint64_t&>(d))
+      : "l"(reinterpret_cast<uint64_t&>(a)), "l"(reinterpret_cast<uint64_t&>(b)));
+  return d;
+}
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -91,6 +103,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  if (warp < 4) reg_dealloc<80>();
   if (warp == 0) {
     if (lane == 0) {
       mbar_expect_tx(&q_full[0], ATT_TILE_BYTES);
@@ -172,6 +185,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
       }
     }
   } else if (warp >= 4) {
+    reg_alloc<216>();
     const int t = (warp - 4) >> 2;
     if (t == 0 || two) {
       const int quarter = warp & 3;
@@ -186,23 +200,25 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
         const int kv_valid = min(128, p.n - j * 128);
         mbar_wait(&s_full[t], j & 1);
         tc_fence_after();
-        // ---- pass 1: row max
-        float mx = -INFINITY;
+        // ---- whole S row (128 fp32) into registers in one shot
+        uint32_t raw[128];
+        tmem_ld32(tS, raw);
+        tmem_ld32(tS + 32, raw + 32);
+        tmem_ld32(tS + 64, raw + 64);
+        tmem_ld32(tS + 96, raw + 96);
+        tmem_ld_wait();
+        if (kv_valid != 128) {
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          uint32_t raw[32];
-          tmem_ld32(tS + c * 32, raw);
-          tmem_ld_wait();
-          if (kv_valid == 128) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(raw[i]));
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (c * 32 + i < kv_valid) mx = fmaxf(mx, __uint_as_float(raw[i]));
-          }
+          for (int i = 0; i < 128; ++i)
+            if (i >= kv_valid) raw[i] = 0xff800000u;   // -inf: excluded from the max, exp2 -> 0
         }
-        const float m_new = fmaxf(m_used, mx);
+        float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 128; i += 4) {
+          mx0 = fmaxf(fmaxf(mx0, __uint_as_float(raw[i])), __uint_as_float(raw[i + 1]));
+          mx1 = fmaxf(fmaxf(mx1, __uint_as_float(raw[i + 2])), __uint_as_float(raw[i + 3]));
+        }
+        const float m_new = fmaxf(m_used, fmaxf(mx0, mx1));
         if (j == 0) {
           m_used = m_new;
         } else {
@@ -227,26 +243,24 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
             tmem_st_wait();
           }
         }
-        // ---- pass 2: P = exp2(S - m), row sum, bf16 pack into the S columns
+        // ---- P = exp2(S - m) (packed f32x2 subtract / accumulate), bf16 pack into the S columns
+        const float2 negm = make_float2(-m_used, -m_used);
+        float2 acc = make_float2(0.f, 0.f);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          uint32_t raw[32];
-          tmem_ld32(tS + c * 32, raw);
-          tmem_ld_wait();
           uint32_t pk[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            float a = ex2_approx(__uint_as_float(raw[2 * i]) - m_used);
-            float b = ex2_approx(__uint_as_float(raw[2 * i + 1]) - m_used);
-            if (kv_valid != 128) {
-              if (c * 32 + 2 * i >= kv_valid) a = 0.f;
-              if (c * 32 + 2 * i + 1 >= kv_valid) b = 0.f;
-            }
-            l += a + b;
-            pk[i] = pack_bf16(a, b);
+            float2 x = make_float2(__uint_as_float(raw[c * 32 + 2 * i]), __uint_as_float(raw[c * 32 + 2 * i + 1]));
+            x = fadd2(x, negm);
+            x.x = ex2_approx(x.x);
+            x.y = ex2_approx(x.y);
+            acc = fadd2(acc, x);
+            pk[i] = pack_bf16(x.x, x.y);
           }
           tmem_st16(tS + c * 16, pk);
         }
+        l += acc.x + acc.y;
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();

@@ -128,7 +128,7 @@ class Engine:
         self.depth_w = _bf(dw.flatten(1))                         # [C, 2*patch*patch], K order (ch, ky, kx)
         self.depth_b = _f32(ag.depth_patch_embed.proj.bias)
         self.ones_c = torch.ones(self.C, device=self.device, dtype=F32)
-        self.dpt = {name: DPTPack(getattr(model, name)) for name in ("depth_head", "point_head")
+        self.dpt_packs = {name: DPTPack(getattr(model, name)) for name in ("depth_head", "point_head")
                     if getattr(model, name, None) is not None}
         self.ws = Workspace(self.device)
         self.attn_events = None      # bench.py sets this to a list to time the global-attention launches
@@ -303,7 +303,7 @@ class Engine:
 
     def dpt(self, name: str, slots: Dict[int, torch.Tensor], layers: Sequence[int], K: int, H: int, W: int,
             head_act: int, chunk: int = 8):
-        pk = self.dpt[name]
+        pk = self.dpt_packs[name]
         preds = torch.empty(K, H, W, pk.outc - 1, device=self.device, dtype=F32)
         conf = torch.empty(K, H, W, device=self.device, dtype=F32)
         sl = [slots[i] for i in layers]

@@ -13,8 +13,12 @@ BF16 = torch.bfloat16
 F32 = torch.float32
 
 
+def _on_device(t: torch.Tensor) -> bool:
+    return t.is_cuda
+
+
 def _chk(t: torch.Tensor, dtype, name: str):
-    if t.dtype != dtype or not t.is_cuda:
+    if t.dtype != dtype or not _on_device(t):
         raise TypeError(f"{name}: expected cuda {dtype}, got {t.device} {t.dtype}")
 
 
@@ -38,7 +42,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, m: Optional[int] = None, taps: Opt
     keep = []
     for k, v in kw.items():
         if isinstance(v, torch.Tensor):
-            assert v.is_cuda and v.is_contiguous(), k
+            assert _on_device(v) and v.is_contiguous(), k
             keep.append(v)
             setattr(g, k, v.data_ptr())
         elif v is not None:
