@@ -103,7 +103,8 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < 4) reg_dealloc<80>();
+  // register budget after the split must stay <= 168 * 384 = 64512 (the launch allocation): 128*72 + 256*208 = 62464
+  if (warp < 4) reg_dealloc<72>();
   if (warp == 0) {
     if (lane == 0) {
       mbar_expect_tx(&q_full[0], ATT_TILE_BYTES);
@@ -185,7 +186,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
       }
     }
   } else if (warp >= 4) {
-    reg_alloc<216>();
+    reg_alloc<208>();
     const int t = (warp - 4) >> 2;
     if (t == 0 || two) {
       const int quarter = warp & 3;

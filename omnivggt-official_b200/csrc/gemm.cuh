@@ -75,6 +75,221 @@ struct GemmCfg {
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 
+// One 128 x BN accumulator tile: TMEM -> registers -> fused epilogue -> global.  `trow` addresses this warp's TMEM lane
+// quarter of the accumulator stage, `m` is this thread's global row, `colhalf` selects which column chunks this warp owns.
+template <int BN, int EPI>
+__device__ __forceinline__ void epilogue_tile(const GemmParams& p, const uint32_t trow, const int m, const int n0,
+                                              const int colhalf, const float* s_rope) {
+  if constexpr (EPI == EPI_QKV) {
+    // ---- per-row RoPE position (reference omnivggt_aggregator.py:215-224; layers/rope.py:39-59)
+    int py = 0, px = 0;
+    {
+      const int t = m % p.T;
+      if (t >= p.nspecial) {
+        const int pp = t - p.nspecial;
+        py = pp / p.wp + 1;
+        px = pp % p.wp + 1;
+      }
+    }
+    const float* cy = s_rope + py * 17;
+    const float* sy = s_rope + 64 * 17 + py * 17;
+    const float* cx = s_rope + px * 17;
+    const float* sx = s_rope + 64 * 17 + px * 17;
+    const long long seq = m / p.ntok;
+    const long long tok = m % p.ntok;
+    const int heads = p.C >> 6;
+    for (int c = colhalf; c < BN / 64; c += 2) {
+      const int n = n0 + c * 64;
+      uint32_t raw[64];
+      tmem_ld32(trow + c * 64, raw);
+      tmem_ld32(trow + c * 64 + 32, raw + 32);
+      tmem_ld_wait();
+      if (m < p.M && n < p.N) {
+        float v[64];
+#pragma unroll
+        for (int i = 0; i < 64; ++i) v[i] = __uint_as_float(raw[i]) + __ldg(p.bias + n + i);
+        const int which = n / p.C;
+        const int h = (n - which * p.C) >> 6;
+        if (which < 2) {
+          const float* w = which == 0 ? p.qn_w : p.kn_w;
+          const float* b = which == 0 ? p.qn_b : p.kn_b;
+          float mean = 0.f;
+#pragma unroll
+          for (int i = 0; i < 64; ++i) mean += v[i];
+          mean *= (1.0f / 64.0f);
+          float var = 0.f;
+#pragma unroll
+          for (int i = 0; i < 64; ++i) {
+            const float d = v[i] - mean;
+            var += d * d;
+          }
+          const float rstd = rsqrtf(var * (1.0f / 64.0f) + 1e-5f);
+#pragma unroll
+          for (int i = 0; i < 64; ++i) v[i] = (v[i] - mean) * rstd * __ldg(w + i) + __ldg(b + i);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float a0 = v[i], b0 = v[i + 16];
+            v[i] = a0 * cy[i] - b0 * sy[i];
+            v[i + 16] = b0 * cy[i] + a0 * sy[i];
+            const float a1 = v[32 + i], b1 = v[48 + i];
+            v[32 + i] = a1 * cx[i] - b1 * sx[i];
+            v[48 + i] = b1 * cx[i] + a1 * sx[i];
+          }
+          if (which == 0) {
+#pragma unroll
+            for (int i = 0; i < 64; ++i) v[i] *= p.qscale;
+          }
+        }
+        __nv_bfloat16* dst = (which == 0 ? p.q_out : (which == 1 ? p.k_out : p.v_out)) +
+                             ((seq * heads + h) * p.ntok + tok) * 64;
+        uint4* d4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          uint4 o;
+          o.x = pack_bf16(v[8 * i + 0], v[8 * i + 1]);
+          o.y = pack_bf16(v[8 * i + 2], v[8 * i + 3]);
+          o.z = pack_bf16(v[8 * i + 4], v[8 * i + 5]);
+          o.w = pack_bf16(v[8 * i + 6], v[8 * i + 7]);
+          d4[i] = o;
+        }
+      }
+    }
+  } else {
+    // ---- row mapping
+    bool row_ok = m < p.M;
+    bool interior = true;  // RM_PAD: border rows are written as zeros
+    long long drow = m;
+    int fr = 0, yy = 0, xx = 0;
+    if (EPI == EPI_RESID) {
+      if (p.row_index && row_ok) drow = p.row_index[m];
+    }
+    if (EPI == EPI_BF16 || EPI == EPI_HEADTAIL) {
+      if (p.rowmap == RM_DENSE2PAD || p.rowmap == RM_PIXSHUF) {
+        const int hw = p.gh * p.gw;
+        fr = m / hw;
+        const int rem = m - fr * hw;
+        yy = rem / p.gw;
+        xx = rem - yy * p.gw;
+        if (p.rowmap == RM_DENSE2PAD)
+          drow = (static_cast<long long>(fr) * (p.gh + 2) + (yy + 1)) * (p.gw + 2) + (xx + 1);
+      } else if (p.rowmap == RM_PAD) {
+        const int pw = p.gw + 2;
+        const int pp = (p.gh + 2) * pw;
+        fr = m / pp;
+        const int rem = m - fr * pp;
+        yy = rem / pw;
+        xx = rem - yy * pw;
+        interior = (yy >= 1 && yy <= p.gh && xx >= 1 && xx <= p.gw);
+      }
+    }
+    for (int c = colhalf; c < BN / 32; c += 2) {
+      const int n = n0 + c * 32;
+      uint32_t raw[32];
+      tmem_ld32(trow + c * 32, raw);
+      tmem_ld_wait();
+      if (!(row_ok && n < p.N)) continue;
+      float v[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
+
+      if constexpr (EPI == EPI_RESID) {
+        float* x = reinterpret_cast<float*>(p.out) + drow * p.ldo + n;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float4 xv = reinterpret_cast<float4*>(x)[i];
+          const float4 g = __ldg(reinterpret_cast<const float4*>(p.gamma + n) + i);
+          const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n) + i);
+          xv.x += g.x * (v[4 * i + 0] + b.x);
+          xv.y += g.y * (v[4 * i + 1] + b.y);
+          xv.z += g.z * (v[4 * i + 2] + b.z);
+          xv.w += g.w * (v[4 * i + 3] + b.w);
+          reinterpret_cast<float4*>(x)[i] = xv;
+        }
+      } else if constexpr (EPI == EPI_HEADTAIL) {
+        if (!interior) continue;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + __ldg(p.bias + i), 0.f);
+        const long long pix = (static_cast<long long>(fr) * p.gh + (yy - 1)) * p.gw + (xx - 1);
+        for (int o = 0; o < p.outc; ++o) {
+          float acc = __ldg(p.b2 + o);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) acc += __ldg(p.w2 + o * 32 + i) * v[i];
+          if (o == p.outc - 1) {
+            p.conf[pix] = 1.0f + expf(acc);
+          } else {
+            const float y = p.head_act == 0 ? expf(acc) : copysignf(expm1f(fabsf(acc)), acc);
+            p.preds[pix * (p.outc - 1) + o] = y;
+          }
+        }
+      } else {  // EPI_BF16
+        int bn = n;      // bias / channel index
+        long long dcol = n;
+        if (p.rowmap == RM_PIXSHUF) {
+          const int kk = n / p.cout;
+          bn = n - kk * p.cout;
+          const int ky = kk / p.ps, kx = kk - ky * p.ps;
+          const int oh = p.gh * p.ps, ow = p.gw * p.ps;
+          drow = (static_cast<long long>(fr) * (oh + 2) + (yy * p.ps + ky + 1)) * (ow + 2) + (xx * p.ps + kx + 1);
+          dcol = bn;
+        }
+        if (p.bias) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] += __ldg(p.bias + bn + i);
+        }
+        if (p.table) {
+          const float* t = p.table + static_cast<long long>(m % p.table_rows) * p.N + n;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] += __ldg(t + i);
+        }
+        const long long off = drow * p.ldo + dcol;
+        if (p.skip1) {
+          const uint4* s4 = reinterpret_cast<const uint4*>(p.skip1 + off);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const uint4 sv = __ldg(s4 + i);
+            v[8 * i + 0] += bf16_lo(sv.x); v[8 * i + 1] += bf16_hi(sv.x);
+            v[8 * i + 2] += bf16_lo(sv.y); v[8 * i + 3] += bf16_hi(sv.y);
+            v[8 * i + 4] += bf16_lo(sv.z); v[8 * i + 5] += bf16_hi(sv.z);
+            v[8 * i + 6] += bf16_lo(sv.w); v[8 * i + 7] += bf16_hi(sv.w);
+          }
+        }
+        if (p.skip2) {
+          const uint4* s4 = reinterpret_cast<const uint4*>(p.skip2 + off);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const uint4 sv = __ldg(s4 + i);
+            v[8 * i + 0] += bf16_lo(sv.x); v[8 * i + 1] += bf16_hi(sv.x);
+            v[8 * i + 2] += bf16_lo(sv.y); v[8 * i + 3] += bf16_hi(sv.y);
+            v[8 * i + 4] += bf16_lo(sv.z); v[8 * i + 5] += bf16_hi(sv.z);
+            v[8 * i + 6] += bf16_lo(sv.w); v[8 * i + 7] += bf16_hi(sv.w);
+          }
+        }
+        if (p.act == 1) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+        } else if (p.act == 2) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+        }
+        if (!interior) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = 0.f;
+        }
+        uint4* d4 = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + off);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint4 o;
+          o.x = pack_bf16(v[8 * i + 0], v[8 * i + 1]);
+          o.y = pack_bf16(v[8 * i + 2], v[8 * i + 3]);
+          o.z = pack_bf16(v[8 * i + 4], v[8 * i + 5]);
+          o.w = pack_bf16(v[8 * i + 6], v[8 * i + 7]);
+          d4[i] = o;
+        }
+      }
+    }
+  }
+}
+
 template <int BN, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
@@ -198,214 +413,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       tc_fence_after();
       const uint32_t trow = tmem_base + as * BN + (static_cast<uint32_t>(quarter * 32) << 16);
 
-      if constexpr (EPI == EPI_QKV) {
-        // ---- per-row RoPE position (reference omnivggt_aggregator.py:215-224; layers/rope.py:39-59)
-        int py = 0, px = 0;
-        {
-          const int t = m % p.T;
-          if (t >= p.nspecial) {
-            const int pp = t - p.nspecial;
-            py = pp / p.wp + 1;
-            px = pp % p.wp + 1;
-          }
-        }
-        const float* cy = s_rope + py * 17;
-        const float* sy = s_rope + 64 * 17 + py * 17;
-        const float* cx = s_rope + px * 17;
-        const float* sx = s_rope + 64 * 17 + px * 17;
-        const long long seq = m / p.ntok;
-        const long long tok = m % p.ntok;
-        const int heads = p.C >> 6;
-        for (int c = colhalf; c < BN / 64; c += 2) {
-          const int n = n0 + c * 64;
-          uint32_t raw[64];
-          tmem_ld32(trow + c * 64, raw);
-          tmem_ld32(trow + c * 64 + 32, raw + 32);
-          tmem_ld_wait();
-          if (m < p.M && n < p.N) {
-            float v[64];
-#pragma unroll
-            for (int i = 0; i < 64; ++i) v[i] = __uint_as_float(raw[i]) + __ldg(p.bias + n + i);
-            const int which = n / p.C;
-            const int h = (n - which * p.C) >> 6;
-            if (which < 2) {
-              const float* w = which == 0 ? p.qn_w : p.kn_w;
-              const float* b = which == 0 ? p.qn_b : p.kn_b;
-              float mean = 0.f;
-#pragma unroll
-              for (int i = 0; i < 64; ++i) mean += v[i];
-              mean *= (1.0f / 64.0f);
-              float var = 0.f;
-#pragma unroll
-              for (int i = 0; i < 64; ++i) {
-                const float d = v[i] - mean;
-                var += d * d;
-              }
-              const float rstd = rsqrtf(var * (1.0f / 64.0f) + 1e-5f);
-#pragma unroll
-              for (int i = 0; i < 64; ++i) v[i] = (v[i] - mean) * rstd * __ldg(w + i) + __ldg(b + i);
-#pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                const float a0 = v[i], b0 = v[i + 16];
-                v[i] = a0 * cy[i] - b0 * sy[i];
-                v[i + 16] = b0 * cy[i] + a0 * sy[i];
-                const float a1 = v[32 + i], b1 = v[48 + i];
-                v[32 + i] = a1 * cx[i] - b1 * sx[i];
-                v[48 + i] = b1 * cx[i] + a1 * sx[i];
-              }
-              if (which == 0) {
-#pragma unroll
-                for (int i = 0; i < 64; ++i) v[i] *= p.qscale;
-              }
-            }
-            __nv_bfloat16* dst = (which == 0 ? p.q_out : (which == 1 ? p.k_out : p.v_out)) +
-                                 ((seq * heads + h) * p.ntok + tok) * 64;
-            uint4* d4 = reinterpret_cast<uint4*>(dst);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              uint4 o;
-              o.x = pack_bf16(v[8 * i + 0], v[8 * i + 1]);
-              o.y = pack_bf16(v[8 * i + 2], v[8 * i + 3]);
-              o.z = pack_bf16(v[8 * i + 4], v[8 * i + 5]);
-              o.w = pack_bf16(v[8 * i + 6], v[8 * i + 7]);
-              d4[i] = o;
-            }
-          }
-        }
-      } else {
-        // ---- row mapping
-        bool row_ok = m < p.M;
-        bool interior = true;  // RM_PAD: border rows are written as zeros
-        long long drow = m;
-        int fr = 0, yy = 0, xx = 0;
-        if (EPI == EPI_RESID) {
-          if (p.row_index && row_ok) drow = p.row_index[m];
-        }
-        if (EPI == EPI_BF16 || EPI == EPI_HEADTAIL) {
-          if (p.rowmap == RM_DENSE2PAD || p.rowmap == RM_PIXSHUF) {
-            const int hw = p.gh * p.gw;
-            fr = m / hw;
-            const int rem = m - fr * hw;
-            yy = rem / p.gw;
-            xx = rem - yy * p.gw;
-            if (p.rowmap == RM_DENSE2PAD)
-              drow = (static_cast<long long>(fr) * (p.gh + 2) + (yy + 1)) * (p.gw + 2) + (xx + 1);
-          } else if (p.rowmap == RM_PAD) {
-            const int pw = p.gw + 2;
-            const int pp = (p.gh + 2) * pw;
-            fr = m / pp;
-            const int rem = m - fr * pp;
-            yy = rem / pw;
-            xx = rem - yy * pw;
-            interior = (yy >= 1 && yy <= p.gh && xx >= 1 && xx <= p.gw);
-          }
-        }
-        for (int c = colhalf; c < BN / 32; c += 2) {
-          const int n = n0 + c * 32;
-          uint32_t raw[32];
-          tmem_ld32(trow + c * 32, raw);
-          tmem_ld_wait();
-          if (!(row_ok && n < p.N)) continue;
-          float v[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
-
-          if constexpr (EPI == EPI_RESID) {
-            float* x = reinterpret_cast<float*>(p.out) + drow * p.ldo + n;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              float4 xv = reinterpret_cast<float4*>(x)[i];
-              const float4 g = __ldg(reinterpret_cast<const float4*>(p.gamma + n) + i);
-              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n) + i);
-              xv.x += g.x * (v[4 * i + 0] + b.x);
-              xv.y += g.y * (v[4 * i + 1] + b.y);
-              xv.z += g.z * (v[4 * i + 2] + b.z);
-              xv.w += g.w * (v[4 * i + 3] + b.w);
-              reinterpret_cast<float4*>(x)[i] = xv;
-            }
-          } else if constexpr (EPI == EPI_HEADTAIL) {
-            if (!interior) continue;
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + __ldg(p.bias + i), 0.f);
-            const long long pix = (static_cast<long long>(fr) * p.gh + (yy - 1)) * p.gw + (xx - 1);
-            for (int o = 0; o < p.outc; ++o) {
-              float acc = __ldg(p.b2 + o);
-#pragma unroll
-              for (int i = 0; i < 32; ++i) acc += __ldg(p.w2 + o * 32 + i) * v[i];
-              if (o == p.outc - 1) {
-                p.conf[pix] = 1.0f + expf(acc);
-              } else {
-                const float y = p.head_act == 0 ? expf(acc) : copysignf(expm1f(fabsf(acc)), acc);
-                p.preds[pix * (p.outc - 1) + o] = y;
-              }
-            }
-          } else {  // EPI_BF16
-            int bn = n;      // bias / channel index
-            long long dcol = n;
-            if (p.rowmap == RM_PIXSHUF) {
-              const int kk = n / p.cout;
-              bn = n - kk * p.cout;
-              const int ky = kk / p.ps, kx = kk - ky * p.ps;
-              const int oh = p.gh * p.ps, ow = p.gw * p.ps;
-              drow = (static_cast<long long>(fr) * (oh + 2) + (yy * p.ps + ky + 1)) * (ow + 2) + (xx * p.ps + kx + 1);
-              dcol = bn;
-            }
-            if (p.bias) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] += __ldg(p.bias + bn + i);
-            }
-            if (p.table) {
-              const float* t = p.table + static_cast<long long>(m % p.table_rows) * p.N + n;
-#pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] += __ldg(t + i);
-            }
-            const long long off = drow * p.ldo + dcol;
-            if (p.skip1) {
-              const uint4* s4 = reinterpret_cast<const uint4*>(p.skip1 + off);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const uint4 sv = __ldg(s4 + i);
-                v[8 * i + 0] += bf16_lo(sv.x); v[8 * i + 1] += bf16_hi(sv.x);
-                v[8 * i + 2] += bf16_lo(sv.y); v[8 * i + 3] += bf16_hi(sv.y);
-                v[8 * i + 4] += bf16_lo(sv.z); v[8 * i + 5] += bf16_hi(sv.z);
-                v[8 * i + 6] += bf16_lo(sv.w); v[8 * i + 7] += bf16_hi(sv.w);
-              }
-            }
-            if (p.skip2) {
-              const uint4* s4 = reinterpret_cast<const uint4*>(p.skip2 + off);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const uint4 sv = __ldg(s4 + i);
-                v[8 * i + 0] += bf16_lo(sv.x); v[8 * i + 1] += bf16_hi(sv.x);
-                v[8 * i + 2] += bf16_lo(sv.y); v[8 * i + 3] += bf16_hi(sv.y);
-                v[8 * i + 4] += bf16_lo(sv.z); v[8 * i + 5] += bf16_hi(sv.z);
-                v[8 * i + 6] += bf16_lo(sv.w); v[8 * i + 7] += bf16_hi(sv.w);
-              }
-            }
-            if (p.act == 1) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
-            } else if (p.act == 2) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
-            }
-            if (!interior) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] = 0.f;
-            }
-            uint4* d4 = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + off);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              uint4 o;
-              o.x = pack_bf16(v[8 * i + 0], v[8 * i + 1]);
-              o.y = pack_bf16(v[8 * i + 2], v[8 * i + 3]);
-              o.z = pack_bf16(v[8 * i + 4], v[8 * i + 5]);
-              o.w = pack_bf16(v[8 * i + 6], v[8 * i + 7]);
-              d4[i] = o;
-            }
-          }
-        }
-      }
+      epilogue_tile<BN, EPI>(p, trow, m, n0, colhalf, s_rope);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[as]);
@@ -420,6 +428,165 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+
+// =====================================================================================================================
+// CTA-pair variant (cta_group::2): one 256 x 256 output tile per 2-SM cluster.  Each CTA stages its own 128 rows of A and
+// 128 of the 256 B rows per K block (32 KB/stage instead of 48 KB for the same FLOPs), which is what matters here: a
+// 128 x 256 single-CTA tile needs ~87 FLOP per L2->SM byte and saturates the L2 fabric (~10-12 TB/s) near 1 PFLOP/s;
+// the paired tile needs 131 FLOP/B.  The pair leader issues M=256 MMAs that write both CTAs' TMEM; every CTA runs its own
+// TMA producer and epilogue (rows [128*rank, 128*rank+128) of the tile).
+constexpr int GEMM2_BN = 256;
+constexpr int GEMM2_STAGES = 6;
+constexpr int GEMM2_B_BYTES = 128 * GEMM_BK * 2;
+constexpr int GEMM2_STAGE_BYTES = GEMM_A_BYTES + GEMM2_B_BYTES;
+constexpr int GEMM2_SMEM_BYTES = GEMM2_STAGES * GEMM2_STAGE_BYTES + 1024 + 256 + 2 * 64 * 17 * 4;
+
+template <int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+  constexpr int BN = GEMM2_BN;
+  constexpr int STAGES = GEMM2_STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * GEMM_A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * GEMM2_STAGE_BYTES);
+  uint64_t* full = bars;                    // used in the leader only: 1 local arrive.expect_tx + 1 remote arrive
+  uint64_t* empty = bars + STAGES;          // per CTA: multicast MMA commit
+  uint64_t* tfull = bars + 2 * STAGES;      // per CTA: multicast MMA commit
+  uint64_t* tempty = bars + 2 * STAGES + 2; // used in the leader only: 8 epilogue warps x 2 CTAs
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  float* s_rope = reinterpret_cast<float*>(smem + STAGES * GEMM2_STAGE_BYTES + 256);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+  const int m_tiles = (p.M + 255) / 256;
+  const int n_tiles = (p.N + BN - 1) / BN;
+  const int num_tiles = m_tiles * n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full[i], 2);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 16);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc_2sm(tmem_slot, 512);
+    tmem_relinquish_2sm();
+  }
+  if (EPI == EPI_QKV && warp >= 2) {
+    for (int i = threadIdx.x - 64; i < p.maxpos * 16; i += GEMM_THREADS - 64) {
+      s_rope[(i >> 4) * 17 + (i & 15)] = p.rope_cos[i];
+      s_rope[64 * 17 + (i >> 4) * 17 + (i & 15)] = p.rope_sin[i];
+    }
+  }
+  tc_fence_before();
+  cluster_sync();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        const int m0 = (tile / n_tiles) * 256 + static_cast<int>(rank) * 128;
+        const int n0 = (tile % n_tiles) * BN + static_cast<int>(rank) * 128;
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+          mbar_wait(&empty[s], ph ^ 1);
+          const uint32_t lead_full = mapa_u32(smem_u32(&full[s]), 0);
+          if (leader) mbar_expect_tx(&full[s], 2 * GEMM2_STAGE_BYTES);
+          else mbar_arrive_cluster(lead_full);
+          const int tap = kb / p.kc_blocks;
+          const int c0 = (kb - tap * p.kc_blocks) * GEMM_BK;
+          tma_load_2d_2sm(sA + s * GEMM_A_BYTES, &tmA, lead_full, c0, m0 + p.tap_off[tap]);
+          tma_load_2d_2sm(sB + s * GEMM2_B_BYTES, &tmB, lead_full, kb * GEMM_BK, n0);
+          if (++s == STAGES) {
+            s = 0;
+            ph ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (pair leader only) =====================
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(256, BN, 0, 0);
+      int s = 0;
+      uint32_t ph = 0;
+      int as = 0;
+      uint32_t aph = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        mbar_wait(&tempty[as], aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint64_t adesc = make_sw128_desc(smem_u32(sA + s * GEMM_A_BYTES));
+          const uint64_t bdesc = make_sw128_desc(smem_u32(sB + s * GEMM2_B_BYTES));
+#pragma unroll
+          for (int k = 0; k < GEMM_BK / 16; ++k)
+            umma_ss_2sm(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit_2sm(&empty[s], 3);
+          if (++s == STAGES) {
+            s = 0;
+            ph ^= 1;
+          }
+        }
+        umma_commit_2sm(&tfull[as], 3);
+        if (++as == 2) {
+          as = 0;
+          aph ^= 1;
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue (8 warps per CTA) =====================
+    const int quarter = warp & 3;
+    const int colhalf = (warp - 2) >> 2;
+    const int r = quarter * 32 + lane;
+    int as = 0;
+    uint32_t aph = 0;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      const int m = (tile / n_tiles) * 256 + static_cast<int>(rank) * 128 + r;
+      const int n0 = (tile % n_tiles) * BN;
+      mbar_wait(&tfull[as], aph);
+      tc_fence_after();
+      const uint32_t trow = tmem_base + as * BN + (static_cast<uint32_t>(quarter * 32) << 16);
+      epilogue_tile<BN, EPI>(p, trow, m, n0, colhalf, s_rope);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (leader) mbar_arrive(&tempty[as]);
+        else mbar_arrive_cluster(mapa_u32(smem_u32(&tempty[as]), 0));
+      }
+      if (++as == 2) {
+        as = 0;
+        aph ^= 1;
+      }
+    }
+  }
+  tc_fence_before();
+  cluster_sync();   // the peer may still signal barriers / read smem of this CTA until both are done
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, 512);
   }
 }
 

@@ -1,5 +1,6 @@
 // libovg C ABI (include/ovg.h): argument validation, TMA descriptor cache, kernel launches.
 #include <atomic>
+#include <cstdlib>
 #include <mutex>
 #include <string>
 #include <unordered_map>
@@ -15,6 +16,7 @@ namespace {
 
 thread_local std::string g_err;
 std::atomic<long long> g_launches{0};
+const bool g_pair_default = [] { const char* e = getenv("OVG_GEMM_PAIR"); return e && e[0] == '1'; }();
 
 int fail(int code, const std::string& msg) {
   g_err = msg;
@@ -126,6 +128,21 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const ovg::GemmPar
   const int grid = tiles < num_sms() ? tiles : num_sms();
   kern<<<grid, ovg::GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, p);
   return post_launch("ovg_gemm");
+}
+
+template <int EPI>
+int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const ovg::GemmParams& p, cudaStream_t st) {
+  static bool attr_set = false;
+  auto kern = ovg::gemm2_kernel<EPI>;
+  if (!attr_set) {
+    OVG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ovg::GEMM2_SMEM_BYTES));
+    attr_set = true;
+  }
+  const int tiles = ((p.M + 255) / 256) * ((p.N + 255) / 256);
+  const int pairs = num_sms() / 2;
+  const int grid = 2 * (tiles < pairs ? tiles : pairs);
+  kern<<<grid, ovg::GEMM_THREADS, ovg::GEMM2_SMEM_BYTES, st>>>(ta, tb, p);
+  return post_launch("ovg_gemm(2sm)");
 }
 
 template <int EPI>
@@ -247,6 +264,20 @@ int ovg_gemm(const ovg_gemm_args* a, void* stream) {
   int rc = get_map(a->a, a->a_cols, a->a_rows, 0, a->lda, 128, &ta);
   if (rc) return rc;
   const unsigned long long ktot = static_cast<unsigned long long>(a->a_cols) * a->num_taps;
+  // block_n 512 selects the CTA-pair kernel (256 x 256 tile per 2-SM cluster); auto-selected for large problems
+  const bool pair = (a->block_n == 512) || (a->block_n == 0 && g_pair_default && a->epi != OVG_EPI_HEADTAIL &&
+                                             a->n >= 256 && a->m >= 512);
+  if (pair) {
+    OVG_REQUIRE(a->epi != OVG_EPI_HEADTAIL, "pair kernel has no HEADTAIL epilogue");
+    rc = get_map(a->b, ktot, a->n, 0, a->ldb, 128, &tb);
+    if (rc) return rc;
+    switch (a->epi) {
+      case OVG_EPI_BF16: return launch_gemm2<ovg::EPI_BF16>(ta, tb, p, st);
+      case OVG_EPI_RESID: return launch_gemm2<ovg::EPI_RESID>(ta, tb, p, st);
+      case OVG_EPI_QKV: return launch_gemm2<ovg::EPI_QKV>(ta, tb, p, st);
+      default: return fail(OVG_E_INVALID, "ovg_gemm: unknown epilogue");
+    }
+  }
   rc = get_map(a->b, ktot, a->n, 0, a->ldb, bn, &tb);
   if (rc) return rc;
 

@@ -29,10 +29,11 @@ GOLDEN = os.path.join(os.path.dirname(HERE), "tests", "golden")
 # model variants -------------------------------------------------------------------------------
 VARIANTS = {
     # conv patchifier, C=128 (2 heads x 64), 4+4 blocks
-    "mini_conv": dict(embed_dim=128, depth=4, patch_embed="conv", features=64,
+    # (DPT channel counts are multiples of 64 -- the tap-GEMM conv needs Cin % 64 == 0, features // 2 included)
+    "mini_conv": dict(embed_dim=128, depth=4, patch_embed="conv", features=128,
                       out_channels=[64, 128, 256, 256], cam_heads=2, cam_trunk=2, img_size=56),
     # reduced DINOv2 patchifier (2 ViT blocks) in front of the same aggregator
-    "mini_dino": dict(embed_dim=128, depth=4, patch_embed="dino", features=64,
+    "mini_dino": dict(embed_dim=128, depth=4, patch_embed="dino", features=128,
                       out_channels=[64, 128, 256, 256], cam_heads=2, cam_trunk=1, img_size=56),
 }
 

@@ -20,7 +20,7 @@ def _worker(rank, world, port, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from omnivggt_official_b200 import OmniVGGT
     from omnivggt_official_b200.dist import broadcast_weights, max_over_ranks, shard_scenes
-    m = OmniVGGT(img_size=56, embed_dim=128, depth=2, patch_embed="conv", dpt_features=64,
+    m = OmniVGGT(img_size=56, embed_dim=128, depth=2, patch_embed="conv", dpt_features=128,
                  dpt_out_channels=(64, 128, 256, 256), dpt_layers=(0, 1, 0, 1), camera_heads=2, camera_trunk_depth=1,
                  init_seed=100 + rank)
     m.randomize_(seed=100 + rank)

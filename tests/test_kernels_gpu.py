@@ -28,7 +28,10 @@ def randn(*s, scale=1.0, seed=0, dtype=F32):
 
 # ----------------------------------------------------------------------------------------------- GEMM
 @pytest.mark.parametrize("M,N,K,bn", [(128, 64, 64, 0), (300, 256, 128, 0), (1000, 384, 192, 128), (2748, 3072, 1024, 256),
-                                      (515, 1024, 4096, 128), (77, 96, 392, 64)])
+                                      (515, 1024, 4096, 128), (77, 96, 392, 64),
+                                      # block_n = 512 selects the CTA-pair (cta_group::2) kernel, 256 x 256 tiles
+                                      (2748, 3072, 1024, 512), (515, 1024, 4096, 512), (300, 256, 128, 512), (129, 512, 64, 512),
+                                      (10992, 1024, 1024, 512)])
 def test_gemm_bf16_bias_gelu(M, N, K, bn):
     ops = _ops()
     a = randn(M, K, seed=1, dtype=BF16)
@@ -42,7 +45,8 @@ def test_gemm_bf16_bias_gelu(M, N, K, bn):
     assert rel(out2, a.float() @ w.float().t()) < 6e-3
 
 
-def test_gemm_resid_rowindex():
+@pytest.mark.parametrize("bn", [0, 512])
+def test_gemm_resid_rowindex(bn):
     ops = _ops()
     M, N, K = 1374 * 2, 1024, 1024
     a = randn(M, K, seed=1, dtype=BF16)
@@ -50,13 +54,13 @@ def test_gemm_resid_rowindex():
     bias, gamma = randn(N, seed=3), randn(N, seed=4)
     x0 = randn(M, N, seed=5)
     x = x0.clone()
-    ops.linear_resid(a, w, bias, gamma, x)
+    ops.linear_resid(a, w, bias, gamma, x, block_n=bn)
     ref = x0 + gamma * (a.float() @ w.float().t() + bias)
     assert rel(x, ref) < 1e-5 + 2e-3 * 0  # fp32 output: only accumulation-order noise
     # scatter rows
     perm = torch.randperm(M, device="cuda", dtype=torch.int32)
     x = x0.clone()
-    ops.linear_resid(a, w, bias, gamma, x, row_index=perm)
+    ops.linear_resid(a, w, bias, gamma, x, row_index=perm, block_n=bn)
     ref2 = x0.clone()
     ref2[perm.long()] += gamma * (a.float() @ w.float().t() + bias)
     assert rel(x, ref2) < 1e-5
@@ -76,8 +80,9 @@ def _rope_ref(t, pos, base=100.0):
     return torch.cat([one(t[..., :32], pos[..., 0]), one(t[..., 32:], pos[..., 1])], -1)
 
 
-@pytest.mark.parametrize("C,frames,hp,wp,S", [(128, 3, 4, 4, 3), (1024, 2, 37, 37, 2), (256, 4, 3, 5, 2)])
-def test_gemm_qkv_epilogue(C, frames, hp, wp, S):
+@pytest.mark.parametrize("C,frames,hp,wp,S,bn", [(128, 3, 4, 4, 3, 0), (1024, 2, 37, 37, 2, 0), (256, 4, 3, 5, 2, 0),
+                                                 (1024, 2, 37, 37, 2, 512), (128, 3, 4, 4, 3, 512)])
+def test_gemm_qkv_epilogue(C, frames, hp, wp, S, bn):
     """QKV linear + q/k LayerNorm(64) + 2-D RoPE + head-major layout vs reference formulas
     (layers/attention.py:52-58, layers/rope.py:154-188)."""
     ops = _ops()
@@ -94,7 +99,7 @@ def test_gemm_qkv_epilogue(C, frames, hp, wp, S):
         nb = M // ntok
         q = torch.zeros(nb, heads, ntok, 64, device="cuda", dtype=BF16)
         k, v = torch.zeros_like(q), torch.zeros_like(q)
-        ops.qkv_proj(a, w, bias, qn_w, qn_b, kn_w, kn_b, q, k, v, ntok=ntok, T=T, nspecial=5, wp=wp, rope_cos=cos, rope_sin=sin)
+        ops.qkv_proj(a, w, bias, qn_w, qn_b, kn_w, kn_b, q, k, v, ntok=ntok, T=T, nspecial=5, wp=wp, rope_cos=cos, rope_sin=sin, block_n=bn)
         qkv = (a.float() @ w.float().t() + bias).reshape(nb, ntok, 3, heads, 64).permute(2, 0, 3, 1, 4)
         yy, xx = torch.meshgrid(torch.arange(hp, device="cuda"), torch.arange(wp, device="cuda"), indexing="ij")
         pos = torch.cat([torch.zeros(5, 2, device="cuda", dtype=torch.long), torch.stack([yy.reshape(-1), xx.reshape(-1)], -1) + 1])
@@ -212,8 +217,9 @@ def _from_pad(p):  # -> NCHW fp32 interior
     return p[:, 1:-1, 1:-1].float().permute(0, 3, 1, 2)
 
 
-@pytest.mark.parametrize("Fr,h,w,Cin,Cout", [(2, 9, 7, 64, 64), (1, 37, 37, 256, 256), (2, 19, 19, 128, 32)])
-def test_conv3x3_taps_with_skips_relu(Fr, h, w, Cin, Cout):
+@pytest.mark.parametrize("Fr,h,w,Cin,Cout,bn", [(2, 9, 7, 64, 64, 0), (1, 37, 37, 256, 256, 0), (2, 19, 19, 128, 32, 0),
+                                                (1, 37, 37, 256, 256, 512), (3, 20, 31, 128, 256, 512)])
+def test_conv3x3_taps_with_skips_relu(Fr, h, w, Cin, Cout, bn):
     """3x3 conv as 9 row-shifted GEMMs over the zero-bordered layout + bias + two skips + ReLU
     (heads/dpt_head.py:379-399)."""
     ops = _ops()
@@ -226,7 +232,7 @@ def test_conv3x3_taps_with_skips_relu(Fr, h, w, Cin, Cout):
     outp = torch.full((Fr, h + 2, w + 2, Cout), 7.0, device="cuda", dtype=BF16)
     taps = [(ky - 1) * (w + 2) + (kx - 1) for ky in range(3) for kx in range(3)]
     ops.gemm(xp.reshape(-1, Cin), wb, taps=taps, epi=ops.L.EPI_BF16, bias=bias, act=ops.L.ACT_RELU, out=outp,
-             ldo=Cout, skip1=s1p, skip2=s2p, rowmap=ops.L.ROWS_PAD, gh=h, gw=w)
+             ldo=Cout, skip1=s1p, skip2=s2p, rowmap=ops.L.ROWS_PAD, gh=h, gw=w, block_n=bn)
     ref = F.relu(F.conv2d(xp[:, 1:-1, 1:-1].float().permute(0, 3, 1, 2), wb.float().reshape(Cout, 3, 3, Cin).permute(0, 3, 1, 2),
                           bias, padding=1) + s1p[:, 1:-1, 1:-1].float().permute(0, 3, 1, 2) + s2p[:, 1:-1, 1:-1].float().permute(0, 3, 1, 2))
     torch.cuda.synchronize()
@@ -236,8 +242,9 @@ def test_conv3x3_taps_with_skips_relu(Fr, h, w, Cin, Cout):
     assert (border == 0).all()         # border rows are rewritten as zeros
 
 
-@pytest.mark.parametrize("ps,Cin,Cout,h,w", [(4, 64, 64, 5, 3), (2, 128, 128, 4, 4), (4, 256, 256, 37, 37)])
-def test_conv_transpose_pixel_shuffle(ps, Cin, Cout, h, w):
+@pytest.mark.parametrize("ps,Cin,Cout,h,w,bn", [(4, 64, 64, 5, 3, 0), (2, 128, 128, 4, 4, 0), (4, 256, 256, 37, 37, 0),
+                                                (4, 256, 256, 37, 37, 512)])
+def test_conv_transpose_pixel_shuffle(ps, Cin, Cout, h, w, bn):
     """ConvTranspose2d(k = s) as one GEMM with a pixel-shuffle store (heads/dpt_head.py:84-89)."""
     ops = _ops()
     Fr = 2
@@ -247,7 +254,7 @@ def test_conv_transpose_pixel_shuffle(ps, Cin, Cout, h, w):
     a = x.permute(0, 2, 3, 1).reshape(-1, Cin).to(BF16).contiguous()
     wb = wt.permute(2, 3, 1, 0).reshape(ps * ps * Cout, Cin).to(BF16).contiguous()
     outp = torch.zeros(Fr, h * ps + 2, w * ps + 2, Cout, device="cuda", dtype=BF16)
-    ops.gemm(a, wb, epi=ops.L.EPI_BF16, bias=bias, out=outp, ldo=Cout, rowmap=ops.L.ROWS_PIXSHUF, gh=h, gw=w, ps=ps, cout=Cout)
+    ops.gemm(a, wb, epi=ops.L.EPI_BF16, bias=bias, out=outp, ldo=Cout, rowmap=ops.L.ROWS_PIXSHUF, gh=h, gw=w, ps=ps, cout=Cout, block_n=bn)
     ref = F.conv_transpose2d(a.float().reshape(Fr, h, w, Cin).permute(0, 3, 1, 2), wb.float().reshape(ps, ps, Cout, Cin).permute(3, 2, 0, 1),
                              bias, stride=ps)
     torch.cuda.synchronize()
