@@ -42,6 +42,35 @@ __device__ __forceinline__ float2 fadd2(float2 a, float2 b) {   // packed fp32x2
       : "l"(reinterpret_cast<uint64_t&>(a)), "l"(reinterpret_cast<uint64_t&>(b)));
   return d;
 }
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {   // packed fp32x2 fma (sm_100 FFMA2)
+  float2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;"
+      : "=l"(reinterpret_cast<uint64_t&>(d))
+      : "l"(reinterpret_cast<uint64_t&>(a)), "l"(reinterpret_cast<uint64_t&>(b)), "l"(reinterpret_cast<uint64_t&>(c)));
+  return d;
+}
+// exp2 on the FMA pipes for a pair of values (x <= ~8): Cody-Waite split x = n + r, r in [-0.5, 0.5], 2^r by a
+// degree-3 minimax polynomial (max rel. error 1.0e-4, far below bf16 resolution of P), exponent inserted with one IMAD.
+// At head_dim 64 the softmax needs 16 384 exp2 per 128x128 tile against 512 tensor-pipe clocks; the MUFU unit alone
+// (16/clk/SM) caps the kernel at 50% tensor utilisation, so a fraction of the exponentials is moved here.
+__device__ __forceinline__ float2 exp2_poly2(float2 x) {
+  const float kMagic = 12582912.0f;   // 1.5 * 2^23: adding it rounds x to the nearest integer in the low mantissa bits
+  x.x = fmaxf(x.x, -126.0f);
+  x.y = fmaxf(x.y, -126.0f);
+  const float2 t = fadd2(x, make_float2(kMagic, kMagic));
+  const float2 n = fadd2(t, make_float2(-kMagic, -kMagic));
+  const float2 r = fadd2(x, make_float2(-n.x, -n.y));
+  float2 p = ffma2(make_float2(0.05500871f, 0.05500871f), r, make_float2(0.24221068f, 0.24221068f));
+  p = ffma2(p, r, make_float2(0.69328292f, 0.69328292f));
+  p = ffma2(p, r, make_float2(1.0f, 1.0f));
+  float2 o;
+  o.x = __int_as_float(__float_as_int(t.x) * 8388608 + __float_as_int(p.x));
+  o.y = __int_as_float(__float_as_int(t.y) * 8388608 + __float_as_int(p.y));
+  return o;
+}
+#ifndef OVG_ATT_EMU_PAIRS
+#define OVG_ATT_EMU_PAIRS 0   // of every 16 element pairs, how many take the polynomial path (0 = all MUFU)
+#endif
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -254,8 +283,12 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
           for (int i = 0; i < 16; ++i) {
             float2 x = make_float2(__uint_as_float(raw[c * 32 + 2 * i]), __uint_as_float(raw[c * 32 + 2 * i + 1]));
             x = fadd2(x, negm);
-            x.x = ex2_approx(x.x);
-            x.y = ex2_approx(x.y);
+            if (i >= 16 - OVG_ATT_EMU_PAIRS) {
+              x = exp2_poly2(x);
+            } else {
+              x.x = ex2_approx(x.x);
+              x.y = ex2_approx(x.y);
+            }
             acc = fadd2(acc, x);
             pk[i] = pack_bf16(x.x, x.y);
           }

@@ -51,25 +51,41 @@ class OmniVGGT(nn.Module, PyTorchModelHubMixin):
         if init_seed is not None:
             init_parameters(self, init_seed, dezero=False)
         self._engine = None
+        object.__setattr__(self, "_dino_lp", None)   # low-precision replica of the frozen patchifier (lazy, not in state_dict)
 
     # ---------------------------------------------------------------------------------------------- packing
     def randomize_(self, seed: int = 0, dezero: bool = True) -> "OmniVGGT":
         """Synthetic weights on the current device (benchmarks / smoke test; there is no checkpoint offline)."""
         init_parameters(self, seed, dezero)
-        self._engine = None
+        self._invalidate()
         return self
 
-    def _load_from_state_dict(self, *a, **k):  # invalidate packed weights on any (re)load
+    def _invalidate(self):
         self._engine = None
+        object.__setattr__(self, "_dino_lp", None)
+
+    def _load_from_state_dict(self, *a, **k):  # invalidate packed weights on any (re)load
+        self._invalidate()
         return super()._load_from_state_dict(*a, **k)
 
     def load_state_dict(self, *a, **k):
-        self._engine = None
+        self._invalidate()
         return super().load_state_dict(*a, **k)
 
     def _apply(self, fn, *a, **k):
-        self._engine = None
+        self._invalidate()
         return super()._apply(fn, *a, **k)
+
+    def _dino_module(self):
+        """The frozen patchifier in ``dino_dtype``: a cached cast of the fp32 master weights (no per-call casts)."""
+        pe = self.aggregator.patch_embed
+        if self.dino_dtype == torch.float32:
+            return pe
+        if self._dino_lp is None:
+            import copy
+            lp = copy.deepcopy(pe).to(self.dino_dtype)
+            object.__setattr__(self, "_dino_lp", lp)          # plain attribute: keep it out of parameters()/state_dict()
+        return self._dino_lp
 
     def engine(self):
         """Repack weights into kernel layouts (bf16, K-major, folded LayerNorm affines) on first use."""
@@ -106,7 +122,7 @@ class OmniVGGT(nn.Module, PyTorchModelHubMixin):
         # ---- frozen patchifier (PyTorch): normalise, DINOv2 / conv patch embed       (omnivggt_aggregator.py:143-150)
         img = ((images.float() - self._resnet_mean) / self._resnet_std).view(K, Cin, H, W)
         if hasattr(ag.patch_embed, "blocks"):
-            patch = TP.dino_patchify(ag.patch_embed, img, self.patch_size, self.dino_dtype)
+            patch = TP.dino_patchify(self._dino_module(), img, self.patch_size, self.dino_dtype)
         else:
             pe = ag.patch_embed.proj
             patch = torch.nn.functional.conv2d(img, pe.weight, pe.bias, stride=self.patch_size).flatten(2).transpose(1, 2)

@@ -17,9 +17,13 @@ lines = []
 for n in nodes:
     t0 = time.time()
     try:
-        r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", n, "--no-header", "-p", "no:cacheprovider"],
+        r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-s", "-m", "gpu", n, "--no-header", "-p", "no:cacheprovider"],
                            cwd=ROOT, capture_output=True, text=True, timeout=240)
         ok = r.returncode == 0
+        for l in r.stdout.splitlines():
+            if '{"' in l and len(l) < 600:
+                print(l, flush=True)
+                lines.append(l)
         tail = "" if ok else "\n".join((r.stdout + r.stderr).splitlines()[-25:])
     except subprocess.TimeoutExpired:
         ok, tail = False, "TIMEOUT"
