@@ -72,8 +72,10 @@ typedef struct ovg_gemm_args {
   const float* rope_cos; const float* rope_sin; float qscale;
   /* OVG_EPI_HEADTAIL */
   const float* w2; const float* b2; int outc; int head_act; float* preds; float* conf;
-  /* tuning: 0 = auto, else 32/64/128/256 */
+  /* tuning: 0 = auto, else 64/128/256, 512 = CTA-pair kernel (256 x 256 tile per 2-SM cluster) */
   int block_n;
+  /* OVG_EPI_QKV switches: q/k LayerNorm(64) and 2-D RoPE (both 1 for aggregator blocks, 0 for DINOv2 blocks) */
+  int qk_norm; int rope;
 } ovg_gemm_args;
 
 int ovg_gemm(const ovg_gemm_args* args, void* stream);
@@ -83,11 +85,11 @@ int ovg_gemm(const ovg_gemm_args* args, void* stream);
  * Replaces F.scaled_dot_product_attention, layers/attention.py:61-66. */
 int ovg_attention(const void* q, const void* k, const void* v, void* out, int batch, int heads, int n, void* stream);
 
-/* LayerNorm over the last dim, fp32 or bf16 in -> bf16 out, optional affine, optional row gather
+/* LayerNorm over the last dim, fp32 or bf16 in -> bf16 (or fp32) out, optional affine, optional row gather
  * (out row m <- in row (m / grp_out) * grp_in + grp_off + m % grp_out; grp_out = 0: identity).
  * layers/block.py:50,:67 (eps 1e-5); heads/dpt_head.py:66,:219-227. */
-int ovg_layernorm(const void* in, int in_is_bf16, long long ld_in, void* out, long long ld_out, int rows, int C,
-                  const float* w, const float* b, float eps, int grp_out, int grp_in, int grp_off, void* stream);
+int ovg_layernorm(const void* in, int in_is_bf16, long long ld_in, void* out, int out_is_f32, long long ld_out, int rows,
+                  int C, const float* w, const float* b, float eps, int grp_out, int grp_in, int grp_off, void* stream);
 
 /* Token assembly + modality scatter (omnivggt_aggregator.py:155-156,:202-213; aggregator.py:343-366). */
 int ovg_assemble_tokens(float* x, const float* patch, const float* cam_tok, const float* reg_tok, const float* inj0,
@@ -104,6 +106,12 @@ int ovg_inject_snapshot(float* x, const float* inj, void* slot, float* cam_out, 
  * layers/patch_embed.py:65-77).  scratch: B * 128 * 2 doubles. */
 int ovg_depth_im2col(const float* depth, const float* mask, const int* idx, double* scratch, void* cols, int ldc,
                      int B, int S, int Sd, int H, int W, int patch, void* stream);
+
+/* RGB patch im2col for the DINOv2 patch embedding (layers/patch_embed.py:65-77, conv k = s = patch): images fp32
+ * [K,3,H,W] in [0,1] are normalised with (x - mean[c]) / std[c] (models/omnivggt_aggregator.py:143) and written as bf16
+ * rows (k, py, px) x cols (c, ky, kx), zero-padded to ldc columns.  mean3 / std3 are HOST arrays of 3 floats. */
+int ovg_image_im2col(const float* images, const float* mean3, const float* std3, void* cols, int ldc, int K, int H, int W,
+                     int patch, void* stream);
 
 /* im2col for the stride-2 3x3 conv (heads/dpt_head.py:93-95): bf16 NHWC [F,h,w,C] -> [F*oh*ow, 9*C]. */
 int ovg_im2col3x3s2(const void* src, void* dst, int F, int h, int w, int C, void* stream);

@@ -36,7 +36,7 @@ class GemmArgs(C.Structure):
         ("qn_w", _vp), ("qn_b", _vp), ("kn_w", _vp), ("kn_b", _vp),
         ("rope_cos", _vp), ("rope_sin", _vp), ("qscale", _f),
         ("w2", _vp), ("b2", _vp), ("outc", _i), ("head_act", _i), ("preds", _vp), ("conf", _vp),
-        ("block_n", _i),
+        ("block_n", _i), ("qk_norm", _i), ("rope", _i),
     ]
 
 
@@ -47,7 +47,8 @@ EXPORTS = {
     "ovg_launch_count": (C.c_longlong, []),
     "ovg_gemm": (C.c_int, [C.POINTER(GemmArgs), _vp]),
     "ovg_attention": (C.c_int, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
-    "ovg_layernorm": (C.c_int, [_vp, _i, _ll, _vp, _ll, _i, _i, _vp, _vp, _f, _i, _i, _i, _vp]),
+    "ovg_layernorm": (C.c_int, [_vp, _i, _ll, _vp, _i, _ll, _i, _i, _vp, _vp, _f, _i, _i, _i, _vp]),
+    "ovg_image_im2col": (C.c_int, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "ovg_assemble_tokens": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "ovg_inject_snapshot": (C.c_int, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "ovg_depth_im2col": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),

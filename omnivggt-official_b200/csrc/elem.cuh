@@ -21,7 +21,8 @@ struct LnParams {
   const void* in;
   int in_bf16;
   long long ld_in;
-  __nv_bfloat16* out;
+  void* out;
+  int out_f32;
   long long ld_out;
   int rows, C;
   const float* w;
@@ -71,7 +72,6 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const LnParams p) {
     q += d * d;
   }
   const float rstd = rsqrtf(warp_sum(q) / p.C + p.eps);
-  __nv_bfloat16* y = p.out + static_cast<long long>(warp) * p.ld_out;
 #pragma unroll
   for (int i = 0; i < VPL / 4; ++i) {
     const int c = (i * 32 + lane) * 4;
@@ -81,10 +81,15 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const LnParams p) {
       o[e] = (v[4 * i + e] - mean) * rstd;
       if (p.w) o[e] = o[e] * __ldg(p.w + c + e) + __ldg(p.b + c + e);
     }
-    uint2 u;
-    u.x = pack_bf16(o[0], o[1]);
-    u.y = pack_bf16(o[2], o[3]);
-    *reinterpret_cast<uint2*>(y + c) = u;
+    if (p.out_f32) {
+      *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + static_cast<long long>(warp) * p.ld_out + c) =
+          make_float4(o[0], o[1], o[2], o[3]);
+    } else {
+      uint2 u;
+      u.x = pack_bf16(o[0], o[1]);
+      u.y = pack_bf16(o[2], o[3]);
+      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<long long>(warp) * p.ld_out + c) = u;
+    }
   }
 }
 
@@ -236,6 +241,34 @@ __global__ void __launch_bounds__(224) depth_im2col_kernel(const DepthParams p) 
     __nv_bfloat16* dst = p.cols + static_cast<long long>(row) * p.ldc;
     dst[e] = __float2bfloat16(d);
     dst[pp + e] = __float2bfloat16(m);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// RGB patch im2col for the DINOv2 patch-embedding GEMM (reference layers/patch_embed.py:65-77) with the ImageNet
+// normalisation of models/omnivggt_aggregator.py:143 fused.  One block per patch; cols (c, ky, kx), zero padded to ldc.
+struct ImageColParams {
+  const float* img;   // [K, 3, H, W]
+  __nv_bfloat16* cols;
+  int ldc, K, H, W, patch;
+  float mean[3], istd[3];
+};
+
+__global__ void __launch_bounds__(256) image_im2col_kernel(const ImageColParams p) {
+  const int hp = p.H / p.patch, wp = p.W / p.patch;
+  const int row = blockIdx.x;
+  const int px = row % wp, py = (row / wp) % hp, k = row / (wp * hp);
+  const int pp = p.patch * p.patch;
+  __nv_bfloat16* dst = p.cols + static_cast<long long>(row) * p.ldc;
+  for (int e = threadIdx.x; e < p.ldc; e += blockDim.x) {
+    float v = 0.f;
+    if (e < 3 * pp) {
+      const int c = e / pp, r = e - c * pp;
+      const int ky = r / p.patch, kx = r - ky * p.patch;
+      v = (p.img[((static_cast<long long>(k) * 3 + c) * p.H + (py * p.patch + ky)) * p.W + (px * p.patch + kx)] - p.mean[c]) *
+          p.istd[c];
+    }
+    dst[e] = __float2bfloat16(v);
   }
 }
 

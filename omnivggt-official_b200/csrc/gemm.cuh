@@ -50,6 +50,8 @@ struct GemmParams {
   const float* rope_cos;  // [maxpos][16]
   const float* rope_sin;
   float qscale;  // softmax scale * log2(e), folded into q
+  int qk_norm;   // 1: LayerNorm(64) on q,k (aggregator blocks); 0: plain (DINOv2 blocks)
+  int rope;      // 1: 2-D RoPE on q,k
   // ---- EPI_HEADTAIL (heads/dpt_head.py:121-126 + heads/head_act.py:61-112): relu, 1x1 32->outc, activation
   const float* w2;  // [outc][32]
   const float* b2;  // [outc]
@@ -73,7 +75,23 @@ struct GemmCfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 2 * 64 * 17 * 4;
 };
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// Exact-erf GELU (nn.GELU() default, reference layers/mlp.py:22,:36) with erf evaluated by Abramowitz-Stegun 7.1.26
+// (|abs err| <= 1.5e-7, three orders below the bf16 output resolution) on 2 MUFU + ~12 FMA-pipe instructions; erff()
+// costs ~3x more and made the fc1 epilogue longer than its K = 1024 mainloop.
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  poly *= t;
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * z * -1.4426950408889634f));
+  const float erf_abs = fmaf(-poly, e, 1.0f);
+  return 0.5f * x * (1.0f + copysignf(erf_abs, x));
+}
 
 // One 128 x BN accumulator tile: TMEM -> registers -> fused epilogue -> global.  `trow` addresses this warp's TMEM lane
 // quarter of the accumulator stage, `m` is this thread's global row, `colhalf` selects which column chunks this warp owns.
@@ -106,11 +124,20 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const uint32_
       tmem_ld_wait();
       if (m < p.M && n < p.N) {
         float v[64];
+        {
+          const float4* b4 = reinterpret_cast<const float4*>(p.bias + n);
 #pragma unroll
-        for (int i = 0; i < 64; ++i) v[i] = __uint_as_float(raw[i]) + __ldg(p.bias + n + i);
+          for (int i = 0; i < 16; ++i) {
+            const float4 b = __ldg(b4 + i);
+            v[4 * i + 0] = __uint_as_float(raw[4 * i + 0]) + b.x;
+            v[4 * i + 1] = __uint_as_float(raw[4 * i + 1]) + b.y;
+            v[4 * i + 2] = __uint_as_float(raw[4 * i + 2]) + b.z;
+            v[4 * i + 3] = __uint_as_float(raw[4 * i + 3]) + b.w;
+          }
+        }
         const int which = n / p.C;
         const int h = (n - which * p.C) >> 6;
-        if (which < 2) {
+        if (which < 2 && p.qk_norm) {
           const float* w = which == 0 ? p.qn_w : p.kn_w;
           const float* b = which == 0 ? p.qn_b : p.kn_b;
           float mean = 0.f;
@@ -125,7 +152,16 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const uint32_
           }
           const float rstd = rsqrtf(var * (1.0f / 64.0f) + 1e-5f);
 #pragma unroll
-          for (int i = 0; i < 64; ++i) v[i] = (v[i] - mean) * rstd * __ldg(w + i) + __ldg(b + i);
+          for (int i = 0; i < 16; ++i) {
+            const float4 w4 = __ldg(reinterpret_cast<const float4*>(w) + i);
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(b) + i);
+            v[4 * i + 0] = (v[4 * i + 0] - mean) * rstd * w4.x + b4.x;
+            v[4 * i + 1] = (v[4 * i + 1] - mean) * rstd * w4.y + b4.y;
+            v[4 * i + 2] = (v[4 * i + 2] - mean) * rstd * w4.z + b4.z;
+            v[4 * i + 3] = (v[4 * i + 3] - mean) * rstd * w4.w + b4.w;
+          }
+        }
+        if (which < 2 && p.rope) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const float a0 = v[i], b0 = v[i + 16];
@@ -135,10 +171,10 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const uint32_
             v[32 + i] = a1 * cx[i] - b1 * sx[i];
             v[48 + i] = b1 * cx[i] + a1 * sx[i];
           }
-          if (which == 0) {
+        }
+        if (which == 0) {
 #pragma unroll
-            for (int i = 0; i < 64; ++i) v[i] *= p.qscale;
-          }
+          for (int i = 0; i < 64; ++i) v[i] *= p.qscale;
         }
         __nv_bfloat16* dst = (which == 0 ? p.q_out : (which == 1 ? p.k_out : p.v_out)) +
                              ((seq * heads + h) * p.ntok + tok) * 64;
@@ -454,7 +490,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * GEMM_A_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * GEMM2_STAGE_BYTES);
-  uint64_t* full = bars;                    // used in the leader only: 1 local arrive.expect_tx + 1 remote arrive
+  uint64_t* full = bars;                    // used in the leader only: its arrive.expect_tx covers both CTAs' bytes
   uint64_t* empty = bars + STAGES;          // per CTA: multicast MMA commit
   uint64_t* tfull = bars + 2 * STAGES;      // per CTA: multicast MMA commit
   uint64_t* tempty = bars + 2 * STAGES + 2; // used in the leader only: 8 epilogue warps x 2 CTAs
@@ -475,7 +511,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int i = 0; i < STAGES; ++i) {
-      mbar_init(&full[i], 2);
+      mbar_init(&full[i], 1);
       mbar_init(&empty[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
@@ -510,8 +546,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         for (int kb = 0; kb < p.k_blocks; ++kb) {
           mbar_wait(&empty[s], ph ^ 1);
           const uint32_t lead_full = mapa_u32(smem_u32(&full[s]), 0);
+          // Only the leader arrives; the peer's TMA bytes are accounted for by the leader's expect_tx (the transaction
+          // count may go transiently negative, which mbarrier allows).  The peer cannot run a phase ahead: it refills
+          // stage s only after the MMA that consumed the previous fill has committed to its empty[s].
           if (leader) mbar_expect_tx(&full[s], 2 * GEMM2_STAGE_BYTES);
-          else mbar_arrive_cluster(lead_full);
           const int tap = kb / p.kc_blocks;
           const int c0 = (kb - tap * p.kc_blocks) * GEMM_BK;
           tma_load_2d_2sm(sA + s * GEMM_A_BYTES, &tmA, lead_full, c0, m0 + p.tap_off[tap]);

@@ -220,6 +220,8 @@ int ovg_gemm(const ovg_gemm_args* a, void* stream) {
   p.rope_cos = a->rope_cos;
   p.rope_sin = a->rope_sin;
   p.qscale = a->qscale;
+  p.qk_norm = a->qk_norm;
+  p.rope = a->rope;
   p.w2 = a->w2;
   p.b2 = a->b2;
   p.outc = a->outc;
@@ -246,9 +248,13 @@ int ovg_gemm(const ovg_gemm_args* a, void* stream) {
     }
   }
   if (a->epi == OVG_EPI_QKV) {
-    OVG_REQUIRE(a->q_out && a->k_out && a->v_out && a->bias && a->qn_w && a->qn_b && a->kn_w && a->kn_b, "QKV args");
-    OVG_REQUIRE(a->rope_cos && a->rope_sin && a->maxpos > 0 && a->maxpos <= 64, "QKV rope table (maxpos <= 64)");
-    OVG_REQUIRE(a->C % 64 == 0 && a->n == 3 * a->C && a->ntok > 0 && a->T > 0 && a->wp > 0, "QKV geometry");
+    OVG_REQUIRE(a->q_out && a->k_out && a->v_out && a->bias, "QKV args");
+    if (a->qk_norm) OVG_REQUIRE(a->qn_w && a->qn_b && a->kn_w && a->kn_b, "QKV q/k norm weights");
+    if (a->rope) OVG_REQUIRE(a->rope_cos && a->rope_sin && a->maxpos > 0 && a->maxpos <= 64 && a->wp > 0,
+                             "QKV rope table (maxpos <= 64)");
+    else p.maxpos = 0;
+    OVG_REQUIRE(a->C % 64 == 0 && a->n == 3 * a->C && a->ntok > 0 && a->T > 0, "QKV geometry");
+    if (p.wp <= 0) p.wp = 1;
     OVG_REQUIRE(a->m % a->ntok == 0, "m must be a multiple of ntok");
     if (bn < 64) bn = 64;
   } else if (a->epi == OVG_EPI_RESID) {
@@ -313,13 +319,13 @@ int ovg_attention(const void* q, const void* k, const void* v, void* out, int ba
   return post_launch("ovg_attention");
 }
 
-int ovg_layernorm(const void* in, int in_is_bf16, long long ld_in, void* out, long long ld_out, int rows, int C,
-                  const float* w, const float* b, float eps, int grp_out, int grp_in, int grp_off, void* stream) {
+int ovg_layernorm(const void* in, int in_is_bf16, long long ld_in, void* out, int out_is_f32, long long ld_out, int rows,
+                  int C, const float* w, const float* b, float eps, int grp_out, int grp_in, int grp_off, void* stream) {
   OVG_REQUIRE(in && out && rows > 0, "null operand");
   OVG_REQUIRE((w == nullptr) == (b == nullptr), "affine needs both weight and bias");
   OVG_REQUIRE(C % 128 == 0 && C <= 2048, "C must be a multiple of 128, <= 2048");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  ovg::LnParams p{in, in_is_bf16, ld_in, reinterpret_cast<__nv_bfloat16*>(out), ld_out, rows, C, w, b, eps,
+  ovg::LnParams p{in, in_is_bf16, ld_in, out, out_is_f32, ld_out, rows, C, w, b, eps,
                   grp_out, grp_in, grp_off};
   const int blocks = (rows + 7) / 8;
   switch (C / 32) {
@@ -368,6 +374,19 @@ int ovg_depth_im2col(const float* depth, const float* mask, const int* idx, doub
   const int rows = B * Sd * (H / patch) * (W / patch);
   ovg::depth_im2col_kernel<<<rows, 224, 0, st>>>(p);
   return post_launch("ovg_depth_im2col");
+}
+
+int ovg_image_im2col(const float* images, const float* mean3, const float* std3, void* cols, int ldc, int K, int H, int W,
+                     int patch, void* stream) {
+  OVG_REQUIRE(images && mean3 && std3 && cols, "null operand");
+  OVG_REQUIRE(K > 0 && H % patch == 0 && W % patch == 0 && ldc >= 3 * patch * patch && ldc % 8 == 0, "bad geometry");
+  ovg::ImageColParams p{images, reinterpret_cast<__nv_bfloat16*>(cols), ldc, K, H, W, patch, {}, {}};
+  for (int c = 0; c < 3; ++c) {
+    p.mean[c] = mean3[c];
+    p.istd[c] = 1.0f / std3[c];
+  }
+  ovg::image_im2col_kernel<<<K * (H / patch) * (W / patch), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  return post_launch("ovg_image_im2col");
 }
 
 int ovg_im2col3x3s2(const void* src, void* dst, int F, int h, int w, int C, void* stream) {

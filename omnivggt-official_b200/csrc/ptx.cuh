@@ -130,8 +130,10 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
   return r;
 }
+// Remote arrive with the default (.release.cta) semantics: ordering of the TMEM reads that precede it is provided by
+// tcgen05.fence::before_thread_sync; a cluster-scope release here costs a full memory fence per call.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // 2-SM TMA load: data lands in this CTA's smem, complete_tx is signalled on `bar_cluster_addr` (the pair leader's barrier)
 __device__ __forceinline__ void tma_load_2d_2sm(void* dst, const CUtensorMap* map, uint32_t bar_cluster_addr, int c0,

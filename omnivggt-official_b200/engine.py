@@ -11,7 +11,7 @@ import torch
 
 from . import _lib as L
 from . import ops
-from .torch_parts import uv_posembed_table
+from .torch_parts import pack_injection, uv_posembed_table
 
 BF16, F32 = torch.bfloat16, torch.float32
 
@@ -40,8 +40,10 @@ class BlockPack:
 
 def pack_block(bp) -> BlockPack:
     a = bp.attn
+    qk = hasattr(a, "q_norm")       # aggregator blocks have q/k LayerNorm; DINOv2 blocks do not
     return BlockPack(_f32(bp.norm1.weight), _f32(bp.norm1.bias), _bf(a.qkv.weight), _f32(a.qkv.bias),
-                     _f32(a.q_norm.weight), _f32(a.q_norm.bias), _f32(a.k_norm.weight), _f32(a.k_norm.bias),
+                     _f32(a.q_norm.weight) if qk else None, _f32(a.q_norm.bias) if qk else None,
+                     _f32(a.k_norm.weight) if qk else None, _f32(a.k_norm.bias) if qk else None,
                      _bf(a.proj.weight), _f32(a.proj.bias), _f32(bp.ls1.gamma),
                      _f32(bp.norm2.weight), _f32(bp.norm2.bias), _bf(bp.mlp.fc1.weight), _f32(bp.mlp.fc1.bias),
                      _bf(bp.mlp.fc2.weight), _f32(bp.mlp.fc2.bias), _f32(bp.ls2.gamma))
@@ -128,6 +130,19 @@ class Engine:
         self.depth_w = _bf(dw.flatten(1))                         # [C, 2*patch*patch], K order (ch, ky, kx)
         self.depth_b = _f32(ag.depth_patch_embed.proj.bias)
         self.ones_c = torch.ones(self.C, device=self.device, dtype=F32)
+        self.inj_pack = pack_injection(ag)
+        # frozen DINOv2 patchifier on the same kernels: reference
+        # layers/vision_transformer.py:214-271 -- blocks without RoPE / q-k norm, LayerNorm eps 1e-6, LayerScale gammas
+        self.dino = None
+        pe = ag.patch_embed
+        if hasattr(pe, "blocks") and getattr(model, "dino_backend", "ovg") == "ovg":
+            w = pe.patch_embed.proj.weight.detach().flatten(1)                       # [C, 3*p*p]
+            kpad = (w.shape[1] + 7) // 8 * 8
+            wpad = torch.zeros(w.shape[0], kpad, device=self.device, dtype=BF16)
+            wpad[:, :w.shape[1]] = w.to(BF16)
+            self.dino = dict(blocks=[pack_block(b) for b in pe.blocks], w=wpad, b=_f32(pe.patch_embed.proj.bias),
+                             norm_w=_f32(pe.norm.weight), norm_b=_f32(pe.norm.bias), heads=pe.heads,
+                             nreg=pe.register_tokens.shape[1], kpad=kpad)
         self.dpt_packs = {name: DPTPack(getattr(model, name)) for name in ("depth_head", "point_head")
                     if getattr(model, name, None) is not None}
         self.ws = Workspace(self.device)
@@ -147,8 +162,33 @@ class Engine:
             self._tables[key] = uv_posembed_table(C, h, w, aspect, self.device)
         return self._tables[key]
 
+    # ------------------------------------------------------------------------------------------ DINOv2 patchifier
+    def dino_patchify(self, images: torch.Tensor, pos_embed: torch.Tensor, mean, std) -> torch.Tensor:
+        """images fp32 [K,3,H,W] in [0,1] -> x_norm_patchtokens fp32 [K,P,C] (reference
+        layers/vision_transformer.py:214-271).  pos_embed: fp32 [1, 1+P, C], already interpolated to this grid."""
+        d, ws, C = self.dino, self.ws, self.C
+        K, _, H, W = images.shape
+        hp, wp = H // self.patch, W // self.patch
+        P, nreg = hp * wp, d["nreg"]
+        Td = 1 + nreg + P
+        pe = self.m.aggregator.patch_embed
+        # token assembly: [cls + pos0, registers, pos_patches] broadcast over frames; the patch-embedding GEMM adds on top
+        base = torch.cat([pe.cls_token.float() + pos_embed[:, :1], pe.register_tokens.float(), pos_embed[:, 1:]], 1)
+        x = ws.get("dino_x", (K, Td, C), F32)
+        x.copy_(base.expand(K, -1, -1))
+        cols = ws.get("dino_cols", (K * P, d["kpad"]))
+        ops.image_im2col(images.contiguous(), mean, std, cols, K, H, W, self.patch)
+        rows = ((torch.arange(K, device=self.device) * Td)[:, None] + (1 + nreg) + torch.arange(P, device=self.device)[None])
+        x2 = x.view(K * Td, C)
+        ops.linear_resid(cols, d["w"], d["b"], self.ones_c, x2, row_index=rows.reshape(-1).to(torch.int32))
+        for bp in d["blocks"]:
+            self.block(bp, x2, K, Td, Td, 1, None, eps=1e-6)
+        out = ws.get("dino_out", (K, P, C), F32)
+        ops.layernorm(x2, out.view(K * P, C), d["norm_w"], d["norm_b"], 1e-6, rows=K * P, grp_out=P, grp_in=Td, grp_off=1 + nreg)
+        return out
+
     # ------------------------------------------------------------------------------------------ aggregator
-    def block(self, bp: BlockPack, x2: torch.Tensor, batch: int, ntok: int, T: int, wp: int, rope):
+    def block(self, bp: BlockPack, x2: torch.Tensor, batch: int, ntok: int, T: int, wp: int, rope, eps: float = 1e-5):
         """x += g1 * proj(attn(LN1 x)); x += g2 * fc2(gelu(fc1(LN2 x)))   (reference layers/block.py:81-107)."""
         M, C = x2.shape
         ws = self.ws
@@ -158,9 +198,9 @@ class Engine:
         v = ws.get("v", (batch, self.heads, ntok, 64))
         o = ws.get("o", (M, C))
         h = ws.get("h", (M, 4 * C))
-        ops.layernorm(x2, xn, bp.ln1_w, bp.ln1_b, 1e-5)
+        ops.layernorm(x2, xn, bp.ln1_w, bp.ln1_b, eps)
         ops.qkv_proj(xn, bp.w_qkv, bp.b_qkv, bp.qn_w, bp.qn_b, bp.kn_w, bp.kn_b, q, k, v, ntok=ntok, T=T,
-                     nspecial=self.R + 1, wp=wp, rope_cos=rope[0], rope_sin=rope[1])
+                     nspecial=self.R + 1, wp=wp, rope_cos=rope[0] if rope else None, rope_sin=rope[1] if rope else None)
         if self.attn_events is not None and ntok > T:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
@@ -170,7 +210,7 @@ class Engine:
         else:
             ops.attention(q, k, v, o, batch, self.heads, ntok)
         ops.linear_resid(o, bp.w_proj, bp.b_proj, bp.g1, x2)
-        ops.layernorm(x2, xn, bp.ln2_w, bp.ln2_b, 1e-5)
+        ops.layernorm(x2, xn, bp.ln2_w, bp.ln2_b, eps)
         ops.linear_bf16(xn, bp.w_fc1, bp.b_fc1, act=L.ACT_GELU, out=h)
         ops.linear_resid(h, bp.w_fc2, bp.b_fc2, bp.g2, x2)
 

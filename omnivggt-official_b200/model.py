@@ -35,11 +35,14 @@ class OmniVGGT(nn.Module, PyTorchModelHubMixin):
                  num_register_tokens: int = 4, dpt_features: int = 256,
                  dpt_out_channels: Sequence[int] = (256, 512, 1024, 1024),
                  dpt_layers: Sequence[int] = (4, 11, 17, 23), camera_heads: int = 16, camera_trunk_depth: int = 4,
-                 dino_dtype: torch.dtype = torch.bfloat16, init_seed: Optional[int] = 0):
+                 dino_backend: str = "ovg", dino_dtype: torch.dtype = torch.bfloat16, camera_dtype: torch.dtype = torch.bfloat16,
+                 init_seed: Optional[int] = 0):
         super().__init__()
         self.img_size, self.patch_size, self.embed_dim = img_size, patch_size, embed_dim
         self.dpt_layers = tuple(dpt_layers)
+        self.dino_backend = dino_backend   # "ovg": frozen patchifier on the libovg kernels; "torch": library kernels
         self.dino_dtype = dino_dtype
+        self.camera_dtype = camera_dtype     # precision of the camera-head weight matrices (fp32 selectable)
         pe = "conv" if "conv" in patch_embed else "dino"
         self.aggregator = AggregatorParams(img_size, patch_size, embed_dim, depth, 64, num_register_tokens, pe,
                                            dino_depth, dino_heads)
@@ -63,6 +66,7 @@ class OmniVGGT(nn.Module, PyTorchModelHubMixin):
     def _invalidate(self):
         self._engine = None
         object.__setattr__(self, "_dino_lp", None)
+        TP.clear_lp_cache(self)
 
     def _load_from_state_dict(self, *a, **k):  # invalidate packed weights on any (re)load
         self._invalidate()
@@ -120,27 +124,32 @@ class OmniVGGT(nn.Module, PyTorchModelHubMixin):
         K = B * S
 
         # ---- frozen patchifier (PyTorch): normalise, DINOv2 / conv patch embed       (omnivggt_aggregator.py:143-150)
-        img = ((images.float() - self._resnet_mean) / self._resnet_std).view(K, Cin, H, W)
-        if hasattr(ag.patch_embed, "blocks"):
-            patch = TP.dino_patchify(self._dino_module(), img, self.patch_size, self.dino_dtype)
+        if eng.dino is not None:
+            P = (H // self.patch_size) * (W // self.patch_size)
+            pos = TP.dino_pos_embed(ag.patch_embed, P, H, W, self.patch_size).float()
+            patch = eng.dino_patchify(images.float().view(K, Cin, H, W), pos, _RESNET_MEAN, _RESNET_STD)
         else:
-            pe = ag.patch_embed.proj
-            patch = torch.nn.functional.conv2d(img, pe.weight, pe.bias, stride=self.patch_size).flatten(2).transpose(1, 2)
-        patch = patch.float().contiguous()
+            img = ((images.float() - self._resnet_mean) / self._resnet_std).view(K, Cin, H, W)
+            if hasattr(ag.patch_embed, "blocks"):
+                patch = TP.dino_patchify(self._dino_module(), img, self.patch_size, self.dino_dtype)
+            else:
+                pe = ag.patch_embed.proj
+                patch = torch.nn.functional.conv2d(img, pe.weight, pe.bias, stride=self.patch_size).flatten(2).transpose(1, 2)
+            patch = patch.float().contiguous()
 
         # ---- aux cameras -> pose encoding -> 25 injection vectors (tiny fp32 host math)  (:158-182,:273-287)
         pose = None
         if len(cam_idx):
             ci = torch.tensor(cam_idx, device=images.device)
             pose = TP.aux_pose_encoding(extrinsics.index_select(1, ci), intrinsics.index_select(1, ci), H, W)
-        inj = TP.injection_vectors(ag, pose, cam_idx, B, S)
+        inj = TP.injection_vectors(eng.inj_pack, pose, cam_idx, B, S)
 
         # ---- hot path: aggregator on libovg
         keep = set(self.dpt_layers)
         slots, cam_tokens = eng.aggregate(patch, inj, depth, mask, depth_idx, B, S, H, W, keep)
 
         predictions: Dict[str, object] = {}
-        pose_list = TP.camera_head(self.camera_head, cam_tokens.view(B, S, -1))
+        pose_list = TP.camera_head(self.camera_head, cam_tokens.view(B, S, -1), dtype=self.camera_dtype)
         predictions["pose_enc"] = pose_list[-1]
         predictions["pose_enc_list"] = pose_list
         d, dc = eng.dpt("depth_head", slots, self.dpt_layers, K, H, W, head_act=0)

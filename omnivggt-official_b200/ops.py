@@ -71,10 +71,13 @@ def rope_tables(maxpos: int, device, base: float = 100.0):
     return ang.cos().contiguous(), ang.sin().contiguous()
 
 
-def qkv_proj(a, w, bias, qn_w, qn_b, kn_w, kn_b, q, k, v, *, ntok, T, nspecial, wp, rope_cos, rope_sin, block_n=0):
+def qkv_proj(a, w, bias, qn_w, qn_b, kn_w, kn_b, q, k, v, *, ntok, T, nspecial=0, wp=1, rope_cos=None, rope_sin=None,
+             block_n=0):
+    """QKV linear with fused epilogue.  q/k LayerNorm when qn_w is given, 2-D RoPE when rope tables are given."""
     C = w.shape[1]
     gemm(a, w, epi=L.EPI_QKV, bias=bias, q_out=q, k_out=k, v_out=v, C=C, ntok=ntok, T=T, nspecial=nspecial, wp=wp,
-         maxpos=rope_cos.shape[0], qn_w=qn_w, qn_b=qn_b, kn_w=kn_w, kn_b=kn_b, rope_cos=rope_cos, rope_sin=rope_sin,
+         maxpos=0 if rope_cos is None else rope_cos.shape[0], qn_w=qn_w, qn_b=qn_b, kn_w=kn_w, kn_b=kn_b,
+         rope_cos=rope_cos, rope_sin=rope_sin, qk_norm=int(qn_w is not None), rope=int(rope_cos is not None),
          qscale=(1.0 / math.sqrt(64.0)) * math.log2(math.e), block_n=block_n)
 
 
@@ -87,11 +90,12 @@ def attention(q, k, v, out, batch: int, heads: int, n: int):
 
 
 def layernorm(x, out, w=None, b=None, eps=1e-5, rows=None, grp_out=0, grp_in=0, grp_off=0):
-    assert x.dtype in (F32, BF16) and out.dtype == BF16 and x.stride(-1) == 1 and out.stride(-1) == 1
+    assert x.dtype in (F32, BF16) and out.dtype in (F32, BF16) and x.stride(-1) == 1 and out.stride(-1) == 1
     x2 = x if x.dim() == 2 else x.reshape(-1, x.shape[-1])
     o2 = out if out.dim() == 2 else out.reshape(-1, out.shape[-1])
     rows = o2.shape[0] if rows is None else rows
-    L.check(L.lib().ovg_layernorm(x2.data_ptr(), int(x.dtype == BF16), x2.stride(0), o2.data_ptr(), o2.stride(0), rows,
+    L.check(L.lib().ovg_layernorm(x2.data_ptr(), int(x.dtype == BF16), x2.stride(0), o2.data_ptr(), int(out.dtype == F32),
+                                  o2.stride(0), rows,
                                   o2.shape[1], L.ptr(w), L.ptr(b), eps, grp_out, grp_in, grp_off, L.stream()))
     return out
 
@@ -110,6 +114,15 @@ def inject_snapshot(x, inj, slot, cam_out, K, T, C, coff):
 def depth_im2col(depth, mask, idx, scratch, cols, B, S, Sd, H, W, patch):
     L.check(L.lib().ovg_depth_im2col(depth.data_ptr(), mask.data_ptr(), idx.data_ptr(), scratch.data_ptr(),
                                      cols.data_ptr(), cols.stride(0), B, S, Sd, H, W, patch, L.stream()))
+
+
+def image_im2col(images, mean3, std3, cols, K, H, W, patch):
+    """mean3 / std3: python floats (host side); images fp32 [K,3,H,W]."""
+    import ctypes
+    m = (ctypes.c_float * 3)(*[float(v) for v in mean3])
+    sd = (ctypes.c_float * 3)(*[float(v) for v in std3])
+    L.check(L.lib().ovg_image_im2col(images.data_ptr(), ctypes.cast(m, ctypes.c_void_p), ctypes.cast(sd, ctypes.c_void_p),
+                                     cols.data_ptr(), cols.stride(0), K, H, W, patch, L.stream()))
 
 
 def im2col3x3s2(src, dst, F, h, w, C):

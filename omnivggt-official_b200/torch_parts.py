@@ -21,15 +21,33 @@ def _lin(x, wb):
     return F.linear(x, wb.weight.to(x.dtype), wb.bias.to(x.dtype))
 
 
-def torch_block(bp, x: Tensor, heads: int, eps: float) -> Tensor:
+def _lin_lp(x, wb, dtype):
+    """Linear with weights held in a cached low-precision replica (fp32 in / fp32 out).  The camera-head GEMMs have
+    M = B*S rows (8 at cfg2) and are pure weight streaming: bf16 weights halve the bytes and use the tensor-core GEMV path
+    instead of the fp32 SIMT sgemm."""
+    if dtype == torch.float32:
+        return _lin(x, wb)
+    lp = wb.__dict__.get("_lp")
+    if lp is None or lp[0].dtype != dtype or lp[0].device != wb.weight.device:
+        lp = (wb.weight.detach().to(dtype), wb.bias.detach().to(dtype))
+        wb.__dict__["_lp"] = lp
+    return F.linear(x.to(dtype), lp[0], lp[1]).float()
+
+
+def clear_lp_cache(module):
+    for m in module.modules():
+        m.__dict__.pop("_lp", None)
+
+
+def torch_block(bp, x: Tensor, heads: int, eps: float, lin=_lin) -> Tensor:
     """Pre-LN block without RoPE / QK-norm (reference layers/block.py:81-107 as used by DINOv2 and the camera
     trunk), on library kernels (cuBLAS + SDPA)."""
     Bx, N, C = x.shape
     h = _ln(x, bp.norm1, eps)
-    qkv = _lin(h, bp.attn.qkv).reshape(Bx, N, 3, heads, C // heads).permute(2, 0, 3, 1, 4)
+    qkv = lin(h, bp.attn.qkv).reshape(Bx, N, 3, heads, C // heads).permute(2, 0, 3, 1, 4)
     o = F.scaled_dot_product_attention(qkv[0], qkv[1], qkv[2]).transpose(1, 2).reshape(Bx, N, C)
-    x = x + _lin(o, bp.attn.proj) * bp.ls1.gamma.to(x.dtype)
-    h = _lin(F.gelu(_lin(_ln(x, bp.norm2, eps), bp.mlp.fc1)), bp.mlp.fc2)
+    x = x + lin(o, bp.attn.proj) * bp.ls1.gamma.to(x.dtype)
+    h = lin(F.gelu(lin(_ln(x, bp.norm2, eps), bp.mlp.fc1)), bp.mlp.fc2)
     return x + h * bp.ls2.gamma.to(x.dtype)
 
 
@@ -65,19 +83,21 @@ def dino_patchify(dp, img: Tensor, patch: int, dtype: torch.dtype) -> Tensor:
 
 
 # ------------------------------------------------------------------------------------------------ camera head
-def camera_head(cp, cam_tokens: Tensor, iters: int = 4) -> List[Tensor]:
-    """reference heads/camera_head.py:83-154.  cam_tokens: fp32 [B, S, 2C] (token 0 of the last layer)."""
+def camera_head(cp, cam_tokens: Tensor, iters: int = 4, dtype: torch.dtype = torch.float32) -> List[Tensor]:
+    """reference heads/camera_head.py:83-154.  cam_tokens: fp32 [B, S, 2C] (token 0 of the last layer).
+    ``dtype`` = precision of the large weight matrices (activations, norms, residuals and the pose update stay fp32)."""
+    lin = (lambda x, wb: _lin_lp(x, wb, dtype))
     tok = _ln(cam_tokens, cp.token_norm, 1e-5)
     B, S, C = tok.shape
     pred, outs = None, []
     for _ in range(iters):
         inp = cp.empty_pose_tokens.expand(B, S, -1) if pred is None else pred
-        mod = _lin(F.silu(_lin(inp, cp.embed_pose)), cp.poseLN_modulation["1"])
+        mod = lin(F.silu(_lin(inp, cp.embed_pose)), cp.poseLN_modulation["1"])
         shift, scale, gate = mod.chunk(3, dim=-1)
         h = gate * (F.layer_norm(tok, (C,), None, None, 1e-6) * (1 + scale) + shift) + tok
         for blk in cp.trunk:
-            h = torch_block(blk, h, cp.heads, 1e-5)
-        delta = _lin(F.gelu(_lin(_ln(h, cp.trunk_norm, 1e-5), cp.pose_branch.fc1)), cp.pose_branch.fc2)
+            h = torch_block(blk, h, cp.heads, 1e-5, lin)
+        delta = _lin(F.gelu(lin(_ln(h, cp.trunk_norm, 1e-5), cp.pose_branch.fc1)), cp.pose_branch.fc2)
         pred = delta if pred is None else pred + delta
         outs.append(torch.cat([pred[..., :7], F.relu(pred[..., 7:])], -1))     # heads/head_act.py:12-35
     return outs
@@ -123,14 +143,19 @@ def aux_pose_encoding(extr: Tensor, intr: Tensor, H: int, W: int) -> Tensor:
     return torch.cat([new[:, :, :3, 3], rotmat_to_quat_xyzw(new[:, :, :3, :3]), fov_h[..., None], fov_w[..., None]], -1)
 
 
-def injection_vectors(ap, pose: Optional[Tensor], cam_idx: List[int], B: int, S: int) -> Tensor:
+def pack_injection(ap):
+    """Stack the depth+1 pose-embedding / camera-adapter layers once (weights are frozen at inference)."""
+    return (torch.stack([m.weight for m in ap.pose_embeddings]).float().contiguous(),      # [L+1, C, 9]
+            torch.stack([m.bias for m in ap.pose_embeddings]).float().contiguous(),        # [L+1, C]
+            torch.stack([m.weight for m in ap.camera_adapters]).float().contiguous(),      # [L+1, C, C]
+            torch.stack([m.bias for m in ap.camera_adapters]).float().contiguous())        # [L+1, C]
+
+
+def injection_vectors(pack, pose: Optional[Tensor], cam_idx: List[int], B: int, S: int) -> Tensor:
     """All depth+1 camera injection vectors [L+1, K, C] fp32 in one shot: they depend only on the inputs, not on
     the token stream (reference omnivggt_aggregator.py:172-179,:211,:273-287).  Frames without a camera receive the
-    adapter *bias* (the adapter is applied to a zero row)."""
-    Wp = torch.stack([m.weight for m in ap.pose_embeddings]).float()      # [L+1, C, 9]
-    bp = torch.stack([m.bias for m in ap.pose_embeddings]).float()        # [L+1, C]
-    Wa = torch.stack([m.weight for m in ap.camera_adapters]).float()      # [L+1, C, C]
-    ba = torch.stack([m.bias for m in ap.camera_adapters]).float()        # [L+1, C]
+    adapter *bias* (the adapter is applied to a zero row).  ``pack`` = pack_injection(aggregator params)."""
+    Wp, bp, Wa, ba = pack
     L1, C = ba.shape
     out = ba[:, None, :].expand(L1, B * S, C).clone()
     if pose is not None and len(cam_idx):

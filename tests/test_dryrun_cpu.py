@@ -29,6 +29,20 @@ def dry(monkeypatch):
     return rec
 
 
+def test_launch_sequence_dino_backend(dry):
+    """The frozen DINOv2 patchifier on the libovg kernels: 2 blocks -> 2 attention launches + image im2col + embed GEMM."""
+    from omnivggt_official_b200.engine import Engine
+    m = mini_model("mini_dino").eval()
+    m._engine = Engine(m)
+    assert m._engine.dino is not None
+    inp = make_inputs(1, 2, 42, 70, seed=1)
+    out = m(images=inp["images"])
+    assert out["depth"].shape == (1, 2, 42, 70, 1)
+    n = dry.calls.count
+    assert n("ovg_image_im2col") == 1 and n("ovg_attention") == 2 * 4 + 2
+    assert n("ovg_layernorm") == 4 * 4 + 2 * 2 + 1 + 2 * 4
+
+
 @pytest.mark.parametrize("B,S,H,W,didx,cidx", [(1, 2, 56, 56, [], []), (2, 3, 42, 70, [0, 2], [0, 1]), (1, 9, 28, 28, [4], [0])])
 def test_launch_sequence(dry, B, S, H, W, didx, cidx):
     from omnivggt_official_b200.engine import Engine

@@ -99,7 +99,7 @@ def test_pose_encoding_and_injection_match_oracle():
     pose = TP.aux_pose_encoding(inp["extrinsics"][:, ti], inp["intrinsics"][:, ti], H, W)
     ref = O.pose_encoding(O.normalize_extrinsics(inp["extrinsics"][:, ti]), inp["intrinsics"][:, ti], H, W)
     assert torch.allclose(pose, ref, atol=1e-5)
-    inj = TP.injection_vectors(m.aggregator, pose, idx, B, S)
+    inj = TP.injection_vectors(TP.pack_injection(m.aggregator), pose, idx, B, S)
     C = 128
     rows = (torch.arange(B)[:, None] * S + ti[None]).reshape(-1)
     for layer in (0, 1, 4):
@@ -108,7 +108,7 @@ def test_pose_encoding_and_injection_match_oracle():
         want = O.linear(g, sd, f"aggregator.camera_adapters.{layer}")
         assert torch.allclose(inj[layer], want, atol=1e-4), layer
     # no cameras: bias only, on every frame
-    inj0 = TP.injection_vectors(m.aggregator, None, [], B, S)
+    inj0 = TP.injection_vectors(TP.pack_injection(m.aggregator), None, [], B, S)
     assert torch.allclose(inj0[2], sd["aggregator.camera_adapters.2.bias"].expand(B * S, -1))
     # single selected camera: no scale normalisation (omnivggt_aggregator.py:98)
     p1 = TP.aux_pose_encoding(inp["extrinsics"][:, :1], inp["intrinsics"][:, :1], H, W)

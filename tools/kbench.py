@@ -31,10 +31,11 @@ def timeit(fn, iters=10, warm=3):
 
 
 res = {}
+KB = os.environ.get("KB", "all")
 S, T, C = int(os.environ.get("S", 8)), 1374, 1024
 M = S * T
 a = torch.randn(M, C, device=dev).to(BF16)
-for name, N, K, bns in (("qkv", 3072, 1024, (256, 512)), ("proj", 1024, 1024, (128, 256, 512)), ("fc1", 4096, 1024, (256, 512)), ("fc2", 1024, 4096, (128, 256, 512))):
+for name, N, K, bns in () if KB == "attn" else (("qkv", 3072, 1024, (256, 512)), ("proj", 1024, 1024, (128, 256, 512)), ("fc1", 4096, 1024, (256, 512)), ("fc2", 1024, 4096, (128, 256, 512))):
     x = torch.randn(M, K, device=dev).to(BF16)
     w = (torch.randn(N, K, device=dev) * K ** -0.5).to(BF16)
     bias = torch.randn(N, device=dev)
@@ -58,18 +59,18 @@ ones, zeros = torch.ones(64, device=dev), torch.zeros(64, device=dev)
 cos, sin = ops.rope_tables(38, dev)
 q = torch.empty(1, 16, M, 64, device=dev, dtype=BF16)
 k, v = torch.empty_like(q), torch.empty_like(q)
-for bn in (256, 512):
+for bn in (256, 512) if KB != "attn" else (256,):
     ms = timeit(lambda: ops.qkv_proj(a, w, bias, ones, zeros, ones, zeros, q, k, v, ntok=M, T=T, nspecial=5, wp=37, rope_cos=cos, rope_sin=sin, block_n=bn))
     res[f"gemm_qkv_fused_bn{bn}"] = dict(ms=ms, tflops=2 * M * 3 * C * C / ms / 1e9)
 # DPT-shaped 3x3 conv: 8 frames x 148^2, 256 -> 256
-Fr, hh, ww = 8, 148, 148
+Fr, hh, ww = (8, 148, 148) if KB != "attn" else (1, 8, 8)
 xp = torch.zeros(Fr, hh + 2, ww + 2, 256, device=dev, dtype=BF16)
 xp[:, 1:-1, 1:-1] = torch.randn(Fr, hh, ww, 256, device=dev).to(BF16)
 wc = (torch.randn(256, 9 * 256, device=dev) * (9 * 256) ** -0.5).to(BF16)
 outp = torch.empty_like(xp)
 taps = [(ky - 1) * (ww + 2) + (kx - 1) for ky in range(3) for kx in range(3)]
 bias256 = torch.randn(256, device=dev)
-for bn in (128, 256, 512):
+for bn in (128, 256, 512) if KB != "attn" else ():
     ms = timeit(lambda: ops.gemm(xp.reshape(-1, 256), wc, taps=taps, epi=ops.L.EPI_BF16, bias=bias256, act=ops.L.ACT_RELU, out=outp, ldo=256, rowmap=ops.L.ROWS_PAD, gh=hh, gw=ww, block_n=bn), iters=5)
     res[f"conv3x3_148_bn{bn}"] = dict(ms=ms, tflops=2 * Fr * hh * ww * 256 * 256 * 9 / ms / 1e9)
 # attention: global and frame
