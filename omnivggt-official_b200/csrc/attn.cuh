@@ -7,11 +7,13 @@
 // CTA = 256 query rows (two 128-row tiles, ping-pong) of one (batch, head).  Roles:
 //   warp 0        TMA producer: Q tiles once, K/V tiles through a 4-stage ring
 //   warp 1        MMA issuer:   S_t = Q_t K^T (SS, M128 N128 K64) and O_t += P_t V (TS: P read from TMEM,
-//                               V as MN-major smem operand, M128 N64 K128); issue order PV_t(j), S_t(j+1)
+//                               V as MN-major smem operand, M128 N64 K128); issue order S_t(j+1), PV_t(j)
 //   warps 4-7     softmax for tile 0 (one query row per thread; row = TMEM lane; the whole 128-wide S row is
 //                 held in registers: one TMEM read per element; setmaxnreg moves registers from warps 0-3 here)
 //   warps 8-11    softmax for tile 1
-// TMEM (512 cols): S0 [0,128) S1 [128,256) O0 [256,320) O1 [320,384); P_t (bf16x2) aliases S_t[0,64).
+// TMEM (512 cols): S0 [0,128) S1 [128,256) P0 [256,320) P1 [320,384) O0 [384,448) O1 [448,512).  P is separate from S so
+// that S_t(j+1) can be issued as soon as the softmax warps have S_t(j) in registers (barrier s_taken): the tensor pipe
+// then runs under the exp phase and each softmax warpgroup goes from one KV tile straight into the next.
 // Online softmax with lazy rescaling: O/l are rescaled only when the running max grows by > 8 (log2 units),
 // which is exact (the stale max cancels in O/l) and keeps P <= 256.
 #pragma once
@@ -69,7 +71,7 @@ __device__ __forceinline__ float2 exp2_poly2(float2 x) {
   return o;
 }
 #ifndef OVG_ATT_EMU_PAIRS
-#define OVG_ATT_EMU_PAIRS 0   // of every 16 element pairs, how many take the polynomial path (0 = all MUFU)
+#define OVG_ATT_EMU_PAIRS 4   // of every 16 element pairs, how many take the polynomial path (0 = all MUFU); 4 measured best
 #endif
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
@@ -95,7 +97,8 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
   uint64_t* s_full = v_empty + NS;     // [2]
   uint64_t* p_full = s_full + 2;       // [2]
   uint64_t* o_ready = p_full + 2;      // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_ready + 2);
+  uint64_t* s_taken = o_ready + 2;     // [2]  softmax has the S tile in registers -> S buffer may be overwritten
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_taken + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -114,6 +117,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
       mbar_init(&s_full[i], 1);
       mbar_init(&p_full[i], 4);
       mbar_init(&o_ready[i], 1);
+      mbar_init(&s_taken[i], 4);
     }
     for (int i = 0; i < NS; ++i) {
       mbar_init(&k_full[i], 1);
@@ -162,7 +166,8 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
       constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
       constexpr uint32_t idesc_pv = make_idesc_bf16(128, 64, 0, 1);  // B (=V) is MN-major
       const uint32_t tS[2] = {tmem_base, tmem_base + 128};
-      const uint32_t tO[2] = {tmem_base + 256, tmem_base + 320};
+      const uint32_t tP[2] = {tmem_base + 256, tmem_base + 320};
+      const uint32_t tO[2] = {tmem_base + 384, tmem_base + 448};
       auto issue_S = [&](int t, int stage) {
         const uint64_t adesc = make_sw128_desc(smem_u32(sQ + t * ATT_TILE_BYTES));
         const uint64_t bdesc = make_sw128_desc(smem_u32(sK + stage * ATT_TILE_BYTES));
@@ -174,7 +179,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
         const uint64_t bdesc = make_sw128_desc(smem_u32(sV + stage * ATT_TILE_BYTES));
 #pragma unroll
         for (int k = 0; k < 8; ++k)   // 16 keys per MMA: P advances 8 cols (bf16x2), V advances 16 rows = 2048 B
-          umma_ts(tO[t], tS[t] + 8 * k, bdesc + static_cast<uint64_t>(k) * (2048 >> 4), idesc_pv,
+          umma_ts(tO[t], tP[t] + 8 * k, bdesc + static_cast<uint64_t>(k) * (2048 >> 4), idesc_pv,
                   (j > 0 || k > 0) ? 1u : 0u);
         umma_commit(&o_ready[t]);
       };
@@ -187,31 +192,36 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
         tc_fence_after();
         issue_S(1, 0);
       }
+      umma_commit(&k_empty[0]);
       for (int j = 0; j < nkv; ++j) {
         const int s = j % NS;
         const uint32_t ph = (j / NS) & 1;
         const int sn = (j + 1) % NS;
         const uint32_t phn = ((j + 1) / NS) & 1;
-        const bool more = (j + 1) < nkv;
+        // S(j+1) as soon as the softmax warps hold S(j) in registers: it overlaps their exp/pack phase, so the next
+        // softmax step never waits for the tensor pipe.
+        if (j + 1 < nkv) {
+          mbar_wait(&k_full[sn], phn);
+          mbar_wait(&s_taken[0], j & 1);
+          tc_fence_after();
+          issue_S(0, sn);
+          if (two) {
+            mbar_wait(&s_taken[1], j & 1);
+            tc_fence_after();
+            issue_S(1, sn);
+          }
+          umma_commit(&k_empty[sn]);
+        }
         mbar_wait(&v_full[s], ph);
         mbar_wait(&p_full[0], j & 1);
         tc_fence_after();
         issue_PV(0, s, j);
-        if (more) {
-          mbar_wait(&k_full[sn], phn);
-          tc_fence_after();
-          issue_S(0, sn);
-        }
         if (two) {
           mbar_wait(&p_full[1], j & 1);
           tc_fence_after();
           issue_PV(1, s, j);
-          if (more) issue_S(1, sn);
         }
         umma_commit(&v_empty[s]);
-        // K stage j was last read by S_t(j), issued one iteration earlier (or in the prologue): a commit here
-        // covers it.
-        umma_commit(&k_empty[s]);
       }
     }
   } else if (warp >= 4) {
@@ -223,7 +233,8 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
       const int qrow = q0 + t * 128 + r;
       const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
       const uint32_t tS = tmem_base + t * 128 + lane_off;
-      const uint32_t tO = tmem_base + 256 + t * 64 + lane_off;
+      const uint32_t tP = tmem_base + 256 + t * 64 + lane_off;
+      const uint32_t tO = tmem_base + 384 + t * 64 + lane_off;
       float m_used = -INFINITY;
       float l = 0.f;
       for (int j = 0; j < nkv; ++j) {
@@ -237,6 +248,9 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
         tmem_ld32(tS + 64, raw + 64);
         tmem_ld32(tS + 96, raw + 96);
         tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_taken[t]);   // S buffer free: the MMA warp may start S(j+1)
         if (kv_valid != 128) {
 #pragma unroll
           for (int i = 0; i < 128; ++i)
@@ -252,10 +266,11 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
         if (j == 0) {
           m_used = m_new;
         } else {
+          // PV(j-1) complete: O is stable (rescale below) and P(j-1) has been read (P buffer reusable)
+          mbar_wait(&o_ready[t], (j - 1) & 1);
+          tc_fence_after();
           const bool need = (m_new - m_used) > 8.0f;
           if (__any_sync(0xffffffffu, need)) {
-            mbar_wait(&o_ready[t], (j - 1) & 1);   // PV(j-1) has landed in O
-            tc_fence_after();
             const float alpha = need ? ex2_approx(m_used - m_new) : 1.0f;
             if (need) {
               m_used = m_new;
@@ -292,7 +307,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
             acc = fadd2(acc, x);
             pk[i] = pack_bf16(x.x, x.y);
           }
-          tmem_st16(tS + c * 16, pk);
+          tmem_st16(tP + c * 16, pk);
         }
         l += acc.x + acc.y;
         tmem_st_wait();
