@@ -474,17 +474,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 // 128 x 256 single-CTA tile needs ~87 FLOP per L2->SM byte and saturates the L2 fabric (~10-12 TB/s) near 1 PFLOP/s;
 // the paired tile needs 131 FLOP/B.  The pair leader issues M=256 MMAs that write both CTAs' TMEM; every CTA runs its own
 // TMA producer and epilogue (rows [128*rank, 128*rank+128) of the tile).
-constexpr int GEMM2_BN = 256;
-constexpr int GEMM2_STAGES = 6;
-constexpr int GEMM2_B_BYTES = 128 * GEMM_BK * 2;
-constexpr int GEMM2_STAGE_BYTES = GEMM_A_BYTES + GEMM2_B_BYTES;
-constexpr int GEMM2_SMEM_BYTES = GEMM2_STAGES * GEMM2_STAGE_BYTES + 1024 + 256 + 2 * 64 * 17 * 4;
+template <int BN>
+struct Gemm2Cfg {
+  static constexpr int STAGES = BN >= 256 ? 6 : 8;
+  static constexpr int B_BYTES = (BN / 2) * GEMM_BK * 2;       // each CTA stages half of the B rows
+  static constexpr int STAGE_BYTES = GEMM_A_BYTES + B_BYTES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + 2 * 64 * 17 * 4;
+};
 
-template <int EPI>
+template <int BN, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
-  constexpr int BN = GEMM2_BN;
-  constexpr int STAGES = GEMM2_STAGES;
+  using Cfg2 = Gemm2Cfg<BN>;
+  constexpr int STAGES = Cfg2::STAGES;
+  constexpr int GEMM2_B_BYTES = Cfg2::B_BYTES;
+  constexpr int GEMM2_STAGE_BYTES = Cfg2::STAGE_BYTES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
@@ -521,7 +525,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc_2sm(tmem_slot, 512);
+    tmem_alloc_2sm(tmem_slot, 2 * BN);
     tmem_relinquish_2sm();
   }
   if (EPI == EPI_QKV && warp >= 2) {
@@ -542,7 +546,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       uint32_t ph = 0;
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
         const int m0 = (tile / n_tiles) * 256 + static_cast<int>(rank) * 128;
-        const int n0 = (tile % n_tiles) * BN + static_cast<int>(rank) * 128;
+        const int n0 = (tile % n_tiles) * BN + static_cast<int>(rank) * (BN / 2);
         for (int kb = 0; kb < p.k_blocks; ++kb) {
           mbar_wait(&empty[s], ph ^ 1);
           const uint32_t lead_full = mapa_u32(smem_u32(&full[s]), 0);
@@ -624,7 +628,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   cluster_sync();   // the peer may still signal barriers / read smem of this CTA until both are done
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc_2sm(tmem_base, 512);
+    tmem_dealloc_2sm(tmem_base, 2 * BN);
   }
 }
 

@@ -16,7 +16,7 @@ namespace {
 
 thread_local std::string g_err;
 std::atomic<long long> g_launches{0};
-const bool g_pair_default = [] { const char* e = getenv("OVG_GEMM_PAIR"); return e && e[0] == '1'; }();
+const bool g_pair_default = [] { const char* e = getenv("OVG_GEMM_PAIR"); return !(e && e[0] == '0'); }();   // A/B switch
 
 int fail(int code, const std::string& msg) {
   g_err = msg;
@@ -130,18 +130,19 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const ovg::GemmPar
   return post_launch("ovg_gemm");
 }
 
-template <int EPI>
+template <int BN, int EPI>
 int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const ovg::GemmParams& p, cudaStream_t st) {
+  using Cfg = ovg::Gemm2Cfg<BN>;
   static bool attr_set = false;
-  auto kern = ovg::gemm2_kernel<EPI>;
+  auto kern = ovg::gemm2_kernel<BN, EPI>;
   if (!attr_set) {
-    OVG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ovg::GEMM2_SMEM_BYTES));
+    OVG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
-  const int tiles = ((p.M + 255) / 256) * ((p.N + 255) / 256);
+  const int tiles = ((p.M + 255) / 256) * ((p.N + BN - 1) / BN);
   const int pairs = num_sms() / 2;
   const int grid = 2 * (tiles < pairs ? tiles : pairs);
-  kern<<<grid, ovg::GEMM_THREADS, ovg::GEMM2_SMEM_BYTES, st>>>(ta, tb, p);
+  kern<<<grid, ovg::GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, p);
   return post_launch("ovg_gemm(2sm)");
 }
 
@@ -270,17 +271,27 @@ int ovg_gemm(const ovg_gemm_args* a, void* stream) {
   int rc = get_map(a->a, a->a_cols, a->a_rows, 0, a->lda, 128, &ta);
   if (rc) return rc;
   const unsigned long long ktot = static_cast<unsigned long long>(a->a_cols) * a->num_taps;
-  // block_n 512 selects the CTA-pair kernel (256 x 256 tile per 2-SM cluster); auto-selected for large problems
-  const bool pair = (a->block_n == 512) || (a->block_n == 0 && g_pair_default && a->epi != OVG_EPI_HEADTAIL &&
-                                             a->n >= 256 && a->m >= 512);
+  // block_n 512 / 384 select the CTA-pair kernels (256 x 256 / 256 x 128 tile per 2-SM cluster).  They stage 33% fewer
+  // L2->SM bytes per FLOP than the single-CTA tiles, which is what bounds these GEMMs; auto-selected for large problems.
+  const bool pair = (a->block_n == 512 || a->block_n == 384) ||
+                    (a->block_n == 0 && g_pair_default && a->epi != OVG_EPI_HEADTAIL && a->n >= 128 && a->m >= 1024);
   if (pair) {
     OVG_REQUIRE(a->epi != OVG_EPI_HEADTAIL, "pair kernel has no HEADTAIL epilogue");
-    rc = get_map(a->b, ktot, a->n, 0, a->ldb, 128, &tb);
+    const int pbn = (a->block_n == 384 || (a->block_n == 0 && a->n < 256)) ? 128 : 256;
+    rc = get_map(a->b, ktot, a->n, 0, a->ldb, pbn / 2, &tb);
     if (rc) return rc;
+    if (pbn == 256) {
+      switch (a->epi) {
+        case OVG_EPI_BF16: return launch_gemm2<256, ovg::EPI_BF16>(ta, tb, p, st);
+        case OVG_EPI_RESID: return launch_gemm2<256, ovg::EPI_RESID>(ta, tb, p, st);
+        case OVG_EPI_QKV: return launch_gemm2<256, ovg::EPI_QKV>(ta, tb, p, st);
+        default: return fail(OVG_E_INVALID, "ovg_gemm: unknown epilogue");
+      }
+    }
     switch (a->epi) {
-      case OVG_EPI_BF16: return launch_gemm2<ovg::EPI_BF16>(ta, tb, p, st);
-      case OVG_EPI_RESID: return launch_gemm2<ovg::EPI_RESID>(ta, tb, p, st);
-      case OVG_EPI_QKV: return launch_gemm2<ovg::EPI_QKV>(ta, tb, p, st);
+      case OVG_EPI_BF16: return launch_gemm2<128, ovg::EPI_BF16>(ta, tb, p, st);
+      case OVG_EPI_RESID: return launch_gemm2<128, ovg::EPI_RESID>(ta, tb, p, st);
+      case OVG_EPI_QKV: return launch_gemm2<128, ovg::EPI_QKV>(ta, tb, p, st);
       default: return fail(OVG_E_INVALID, "ovg_gemm: unknown epilogue");
     }
   }

@@ -147,6 +147,7 @@ class Engine:
                     if getattr(model, name, None) is not None}
         self.ws = Workspace(self.device)
         self.attn_events = None      # bench.py sets this to a list to time the global-attention launches
+        self._idx_cache: Dict[tuple, torch.Tensor] = {}   # small device index tensors (no per-call H2D copies)
         self._rope: Dict[int, Tuple[torch.Tensor, torch.Tensor]] = {}
         self._tables: Dict[tuple, torch.Tensor] = {}
 
@@ -155,6 +156,15 @@ class Engine:
         if maxpos not in self._rope:
             self._rope[maxpos] = ops.rope_tables(maxpos, self.device)
         return self._rope[maxpos]
+
+    def cached(self, key: tuple, make) -> torch.Tensor:
+        t = self._idx_cache.get(key)
+        if t is None:
+            if len(self._idx_cache) > 64:
+                self._idx_cache.clear()
+            t = make().to(self.device)
+            self._idx_cache[key] = t
+        return t
 
     def table(self, C: int, h: int, w: int, aspect: float) -> torch.Tensor:
         key = (C, h, w, round(aspect, 9))
@@ -178,9 +188,10 @@ class Engine:
         x.copy_(base.expand(K, -1, -1))
         cols = ws.get("dino_cols", (K * P, d["kpad"]))
         ops.image_im2col(images.contiguous(), mean, std, cols, K, H, W, self.patch)
-        rows = ((torch.arange(K, device=self.device) * Td)[:, None] + (1 + nreg) + torch.arange(P, device=self.device)[None])
+        rows = self.cached(("dino_rows", K, Td, P), lambda: (
+            (torch.arange(K) * Td)[:, None] + (1 + nreg) + torch.arange(P)[None]).reshape(-1).to(torch.int32))
         x2 = x.view(K * Td, C)
-        ops.linear_resid(cols, d["w"], d["b"], self.ones_c, x2, row_index=rows.reshape(-1).to(torch.int32))
+        ops.linear_resid(cols, d["w"], d["b"], self.ones_c, x2, row_index=rows)
         for bp in d["blocks"]:
             self.block(bp, x2, K, Td, Td, 1, None, eps=1e-6)
         out = ws.get("dino_out", (K, P, C), F32)
@@ -225,23 +236,26 @@ class Engine:
         T = P + R + 1
         ws = self.ws
         x = ws.get("x", (K, T, C), F32)
-        has_depth = torch.zeros(K, dtype=torch.int32)
-        if len(depth_idx):
-            has_depth.view(B, S)[:, depth_idx] = 1
-        has_depth = has_depth.to(self.device, non_blocking=True)
+        def _has_depth():
+            h = torch.zeros(B, S, dtype=torch.int32)
+            if len(depth_idx):
+                h[:, depth_idx] = 1
+            return h.reshape(K)
+        has_depth = self.cached(("has_depth", B, S, tuple(depth_idx)), _has_depth)
         ops.assemble_tokens(x, patch_tokens, self.cam_tok, self.reg_tok, inj[0], self.placeholder, has_depth, K, S, T, R, C)
         x2 = x.view(K * T, C)
         if len(depth_idx):
             Sd = len(depth_idx)
-            idx = torch.tensor(depth_idx, dtype=torch.int32, device=self.device)
+            idx = self.cached(("depth_idx", tuple(depth_idx)), lambda: torch.tensor(depth_idx, dtype=torch.int32))
             kk = 2 * self.patch * self.patch
             cols = ws.get("depth_cols", (B * Sd * P, kk))
             scratch = ws.get("depth_scratch", (B * 128 * 2,), torch.float64)
             d32 = depth.reshape(B, S, H, W).to(F32).contiguous()
             m32 = mask.reshape(B, S, H, W).to(F32).contiguous()
             ops.depth_im2col(d32, m32, idx, scratch, cols, B, S, Sd, H, W, self.patch)
-            rows = ((torch.arange(B)[:, None] * S + torch.tensor(depth_idx)[None]) * T)[:, :, None] + (R + 1) + torch.arange(P)[None, None]
-            rows = rows.reshape(-1).to(torch.int32).to(self.device)
+            rows = self.cached(("depth_rows", B, S, T, P, tuple(depth_idx)), lambda: (
+                ((torch.arange(B)[:, None] * S + torch.tensor(depth_idx)[None]) * T)[:, :, None] + (R + 1) +
+                torch.arange(P)[None, None]).reshape(-1).to(torch.int32))
             ops.linear_resid(cols, self.depth_w, self.depth_b, self.ones_c, x2, row_index=rows)
         rope = self.rope(max(hp, wp) + 1)
         slots: Dict[int, torch.Tensor] = {}

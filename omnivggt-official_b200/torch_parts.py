@@ -161,7 +161,7 @@ def injection_vectors(pack, pose: Optional[Tensor], cam_idx: List[int], B: int, 
     if pose is not None and len(cam_idx):
         g = torch.einsum("brn,lcn->lbrc", pose.float(), Wp) + bp[:, None, None, :]      # [L+1,B,Sc,C]
         inj = torch.einsum("lbrc,ldc->lbrd", g, Wa) + ba[:, None, None, :]
-        rows = (torch.arange(B, device=out.device)[:, None] * S + torch.tensor(cam_idx, device=out.device)[None]).reshape(-1)
+        rows = (torch.arange(B)[:, None] * S + torch.tensor(cam_idx)[None]).reshape(-1).to(out.device)
         out[:, rows] = inj.reshape(L1, -1, C)
     return out.contiguous()
 

@@ -31,7 +31,9 @@ def randn(*s, scale=1.0, seed=0, dtype=F32):
                                       (515, 1024, 4096, 128), (77, 96, 392, 64),
                                       # block_n = 512 selects the CTA-pair (cta_group::2) kernel, 256 x 256 tiles
                                       (2748, 3072, 1024, 512), (515, 1024, 4096, 512), (300, 256, 128, 512), (129, 512, 64, 512),
-                                      (10992, 1024, 1024, 512)])
+                                      (10992, 1024, 1024, 512),
+                                      # block_n = 384: CTA-pair kernel with 256 x 128 tiles
+                                      (2748, 384, 192, 384), (1500, 128, 2048, 384), (300, 256, 128, 384)])
 def test_gemm_bf16_bias_gelu(M, N, K, bn):
     ops = _ops()
     a = randn(M, K, seed=1, dtype=BF16)
@@ -218,7 +220,7 @@ def _from_pad(p):  # -> NCHW fp32 interior
 
 
 @pytest.mark.parametrize("Fr,h,w,Cin,Cout,bn", [(2, 9, 7, 64, 64, 0), (1, 37, 37, 256, 256, 0), (2, 19, 19, 128, 32, 0),
-                                                (1, 37, 37, 256, 256, 512), (3, 20, 31, 128, 256, 512)])
+                                                (1, 37, 37, 256, 256, 512), (3, 20, 31, 128, 256, 512), (2, 30, 30, 256, 128, 384)])
 def test_conv3x3_taps_with_skips_relu(Fr, h, w, Cin, Cout, bn):
     """3x3 conv as 9 row-shifted GEMMs over the zero-bordered layout + bias + two skips + ReLU
     (heads/dpt_head.py:379-399)."""

@@ -4,7 +4,7 @@
 plus size-independent properties at the BASELINE image size.
 
 Tolerance.  The kernels compute with bf16 operands and fp32 accumulation (the reference runs fp32), so the bar is stated
-as relative L2 per output: 3e-2 on the reduced configs / full-width model (measured deviations are recorded in
+as relative L2 per output: 2e-2 on the reduced configs / full-width model (measured: <= 1.5e-2, recorded in
 profiles/ and DESIGN.md); pose_enc additionally max-abs 5e-2."""
 import json
 import os
@@ -18,7 +18,7 @@ from oracle.synth import make_inputs, make_state_dict
 
 pytestmark = pytest.mark.gpu
 INDEX = golden_index()
-TOL = 3e-2
+TOL = 2e-2
 KEYS = ("pose_enc", "depth", "depth_conf", "world_points", "world_points_conf")
 
 

@@ -70,7 +70,7 @@ wc = (torch.randn(256, 9 * 256, device=dev) * (9 * 256) ** -0.5).to(BF16)
 outp = torch.empty_like(xp)
 taps = [(ky - 1) * (ww + 2) + (kx - 1) for ky in range(3) for kx in range(3)]
 bias256 = torch.randn(256, device=dev)
-for bn in (128, 256, 512) if KB != "attn" else ():
+for bn in (256, 512) if KB != "attn" else ():
     ms = timeit(lambda: ops.gemm(xp.reshape(-1, 256), wc, taps=taps, epi=ops.L.EPI_BF16, bias=bias256, act=ops.L.ACT_RELU, out=outp, ldo=256, rowmap=ops.L.ROWS_PAD, gh=hh, gw=ww, block_n=bn), iters=5)
     res[f"conv3x3_148_bn{bn}"] = dict(ms=ms, tflops=2 * Fr * hh * ww * 256 * 256 * 9 / ms / 1e9)
 # attention: global and frame
@@ -80,6 +80,17 @@ res["attn_global"] = dict(ms=ms, tflops=4 * M * M * C / ms / 1e9)
 qf, kf, vf = (t.reshape(16, S, T, 64).transpose(0, 1).contiguous() for t in (q, k, v))
 ms = timeit(lambda: ops.attention(qf, kf, vf, o, S, 16, T))
 res["attn_frame"] = dict(ms=ms, tflops=4 * S * T * T * C / ms / 1e9)
+if KB != "attn":
+    # DPT output_conv1-shaped conv: 8 frames x 296^2, 256 -> 128
+    xq = torch.zeros(8, 298, 298, 256, device=dev, dtype=BF16)
+    wq = (torch.randn(128, 9 * 256, device=dev) * (9 * 256) ** -0.5).to(BF16)
+    oq = torch.empty(8, 298, 298, 128, device=dev, dtype=BF16)
+    tq = [(ky - 1) * 298 + (kx - 1) for ky in range(3) for kx in range(3)]
+    b128 = torch.randn(128, device=dev)
+    for bn in (128, 384):
+        ms = timeit(lambda: ops.gemm(xq.reshape(-1, 256), wq, taps=tq, epi=ops.L.EPI_BF16, bias=b128, out=oq, ldo=128, rowmap=ops.L.ROWS_PAD, gh=296, gw=296, block_n=bn), iters=5)
+        res[f"conv3x3_296_n128_bn{bn}"] = dict(ms=ms, tflops=2 * 8 * 296 * 296 * 256 * 128 * 9 / ms / 1e9)
+    del xq, oq
 import torch.nn.functional as F
 ms = timeit(lambda: F.scaled_dot_product_attention(q, k, v), iters=5)
 res["sdpa_global_torch"] = dict(ms=ms, tflops=4 * M * M * C / ms / 1e9)
