@@ -116,10 +116,11 @@ int ovg_image_im2col(const float* images, const float* mean3, const float* std3,
 /* im2col for the stride-2 3x3 conv (heads/dpt_head.py:93-95): bf16 NHWC [F,h,w,C] -> [F*oh*ow, 9*C]. */
 int ovg_im2col3x3s2(const void* src, void* dst, int F, int h, int w, int C, void* stream);
 
-/* Bilinear align_corners=True upsampling between zero-bordered bf16 NHWC maps, optional fp32 additive table
- * [H*W, C] (heads/dpt_head.py:242-250,:466,:472-497). */
-int ovg_upsample_bilinear(const void* src, void* dst, const float* table, int F, int h, int w, int H, int W, int C,
-                          void* stream);
+/* Bilinear align_corners=True upsampling between zero-bordered bf16 NHWC maps (heads/dpt_head.py:242-247,:466,
+ * :472-497) with the optional UV position embedding of heads/dpt_head.py:249-250 given in separable form: tx fp32
+ * [W, C/2] for channels [0, C/2), ty fp32 [H, C/2] for channels [C/2, C) (both NULL: no embedding). */
+int ovg_upsample_bilinear(const void* src, void* dst, const float* tx, const float* ty, int F, int h, int w, int H, int W,
+                          int C, void* stream);
 
 #ifdef __cplusplus
 }

@@ -53,7 +53,7 @@ EXPORTS = {
     "ovg_inject_snapshot": (C.c_int, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "ovg_depth_im2col": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "ovg_im2col3x3s2": (C.c_int, [_vp, _vp, _i, _i, _i, _i, _vp]),
-    "ovg_upsample_bilinear": (C.c_int, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "ovg_upsample_bilinear": (C.c_int, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
 }
 
 _lib: Optional[C.CDLL] = None

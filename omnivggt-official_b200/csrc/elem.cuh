@@ -294,40 +294,41 @@ __global__ void im2col3x3s2_kernel(const Im2colParams p) {
 
 // ---------------------------------------------------------------------------------------------------
 // Bilinear upsampling, align_corners=True (reference heads/dpt_head.py:466,:472-497, F.interpolate), on
-// zero-bordered NHWC bf16 maps: src [F,h+2,w+2,C] -> dst [F,H+2,W+2,C]; optional fp32 additive table
-// [H*W, C] (the x0.1 UV position embedding of heads/dpt_head.py:249-250).  Border pixels are written as 0.
+// zero-bordered NHWC bf16 maps: src [F,h+2,w+2,C] -> dst [F,H+2,W+2,C].  Optional additive UV position embedding
+// (heads/dpt_head.py:249-250): the sin/cos embedding of heads/utils.py:11-108 is separable -- channels [0,C/2) depend on x
+// only, [C/2,C) on y only -- so it is passed as two small tables tx [W, C/2], ty [H, C/2] (x0.1 folded in) instead of an
+// [H*W, C] fp32 map that would have to be streamed from HBM for every frame.  Border pixels are written as 0.
+// Grid (x-chunks, H+2, F): no integer divisions in the index math; each thread moves 8 channels (16 B).
 struct UpsampleParams {
   const __nv_bfloat16* src;
   __nv_bfloat16* dst;
-  const float* table;
+  const float* tx;
+  const float* ty;
   int F, h, w, H, W, C;
+  float sy, sx;
 };
 
 __global__ void __launch_bounds__(256) upsample_bilinear_kernel(const UpsampleParams p) {
-  const int vec = p.C / 8;
-  const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const long long pix = gid / vec;
-  const int cv = static_cast<int>(gid % vec);
-  const long long npix = static_cast<long long>(p.F) * (p.H + 2) * (p.W + 2);
-  if (pix >= npix) return;
-  const int X = static_cast<int>(pix % (p.W + 2));
-  const int Y = static_cast<int>((pix / (p.W + 2)) % (p.H + 2));
-  const int f = static_cast<int>(pix / (static_cast<long long>(p.W + 2) * (p.H + 2)));
+  const int vec = p.C >> 3;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int X = t / vec;
+  const int cv = t - X * vec;
+  if (X >= p.W + 2) return;
+  const int Y = blockIdx.y, f = blockIdx.z;
   uint4 out = make_uint4(0, 0, 0, 0);
   if (X >= 1 && X <= p.W && Y >= 1 && Y <= p.H) {
     const int oy = Y - 1, ox = X - 1;
-    const float sy = p.H > 1 ? static_cast<float>(p.h - 1) / static_cast<float>(p.H - 1) : 0.f;
-    const float sx = p.W > 1 ? static_cast<float>(p.w - 1) / static_cast<float>(p.W - 1) : 0.f;
-    const float fy = sy * oy, fx = sx * ox;
+    const float fy = p.sy * oy, fx = p.sx * ox;
     const int y0 = static_cast<int>(fy), x0 = static_cast<int>(fx);
     const int y1 = y0 + (y0 < p.h - 1 ? 1 : 0), x1 = x0 + (x0 < p.w - 1 ? 1 : 0);
     const float wy1 = fy - y0, wx1 = fx - x0;
     const float wy0 = 1.f - wy1, wx0 = 1.f - wx1;
-    const long long base = static_cast<long long>(f) * (p.h + 2) * (p.w + 2);
-    auto ld = [&](int yy, int xx) {
-      return __ldg(reinterpret_cast<const uint4*>(p.src + (base + static_cast<long long>(yy + 1) * (p.w + 2) + (xx + 1)) * p.C) + cv);
-    };
-    const uint4 a = ld(y0, x0), b = ld(y0, x1), c = ld(y1, x0), d = ld(y1, x1);
+    const __nv_bfloat16* base = p.src + static_cast<size_t>(f) * (p.h + 2) * (p.w + 2) * p.C;
+    const int ws = p.w + 2;
+    const uint4 a = __ldg(reinterpret_cast<const uint4*>(base + static_cast<size_t>((y0 + 1) * ws + (x0 + 1)) * p.C) + cv);
+    const uint4 b = __ldg(reinterpret_cast<const uint4*>(base + static_cast<size_t>((y0 + 1) * ws + (x1 + 1)) * p.C) + cv);
+    const uint4 c = __ldg(reinterpret_cast<const uint4*>(base + static_cast<size_t>((y1 + 1) * ws + (x0 + 1)) * p.C) + cv);
+    const uint4 d = __ldg(reinterpret_cast<const uint4*>(base + static_cast<size_t>((y1 + 1) * ws + (x1 + 1)) * p.C) + cv);
     const uint32_t* ap = &a.x; const uint32_t* bp = &b.x; const uint32_t* cp = &c.x; const uint32_t* dp = &d.x;
     float r[8];
 #pragma unroll
@@ -335,9 +336,11 @@ __global__ void __launch_bounds__(256) upsample_bilinear_kernel(const UpsamplePa
       r[2 * i] = wy0 * (wx0 * bf16_lo(ap[i]) + wx1 * bf16_lo(bp[i])) + wy1 * (wx0 * bf16_lo(cp[i]) + wx1 * bf16_lo(dp[i]));
       r[2 * i + 1] = wy0 * (wx0 * bf16_hi(ap[i]) + wx1 * bf16_hi(bp[i])) + wy1 * (wx0 * bf16_hi(cp[i]) + wx1 * bf16_hi(dp[i]));
     }
-    if (p.table) {
-      const float4* t = reinterpret_cast<const float4*>(p.table + (static_cast<long long>(oy) * p.W + ox) * p.C + cv * 8);
-      const float4 t0 = __ldg(t), t1 = __ldg(t + 1);
+    if (p.tx) {
+      const int half = p.C >> 1;
+      const int c0 = cv * 8;
+      const float* tp = c0 < half ? p.tx + static_cast<size_t>(ox) * half + c0 : p.ty + static_cast<size_t>(oy) * half + (c0 - half);
+      const float4 t0 = __ldg(reinterpret_cast<const float4*>(tp)), t1 = __ldg(reinterpret_cast<const float4*>(tp) + 1);
       r[0] += t0.x; r[1] += t0.y; r[2] += t0.z; r[3] += t0.w;
       r[4] += t1.x; r[5] += t1.y; r[6] += t1.z; r[7] += t1.w;
     }
@@ -346,7 +349,7 @@ __global__ void __launch_bounds__(256) upsample_bilinear_kernel(const UpsamplePa
     out.z = pack_bf16(r[4], r[5]);
     out.w = pack_bf16(r[6], r[7]);
   }
-  *(reinterpret_cast<uint4*>(p.dst + pix * p.C) + cv) = out;
+  *(reinterpret_cast<uint4*>(p.dst + (static_cast<size_t>(f) * (p.H + 2) * (p.W + 2) + static_cast<size_t>(Y) * (p.W + 2) + X) * p.C) + cv) = out;
 }
 
 }  // namespace ovg

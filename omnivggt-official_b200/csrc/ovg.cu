@@ -409,14 +409,18 @@ int ovg_im2col3x3s2(const void* src, void* dst, int F, int h, int w, int C, void
   return post_launch("ovg_im2col3x3s2");
 }
 
-int ovg_upsample_bilinear(const void* src, void* dst, const float* table, int F, int h, int w, int H, int W, int C,
-                          void* stream) {
-  OVG_REQUIRE(src && dst && F > 0 && h > 0 && w > 0 && H > 0 && W > 0 && C % 8 == 0, "bad arguments");
-  ovg::UpsampleParams p{reinterpret_cast<const __nv_bfloat16*>(src), reinterpret_cast<__nv_bfloat16*>(dst), table,
-                        F, h, w, H, W, C};
-  const long long total = static_cast<long long>(F) * (H + 2) * (W + 2) * (C / 8);
-  const long long blocks = (total + 255) / 256;
-  ovg::upsample_bilinear_kernel<<<static_cast<unsigned>(blocks), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+int ovg_upsample_bilinear(const void* src, void* dst, const float* tx, const float* ty, int F, int h, int w, int H, int W,
+                          int C, void* stream) {
+  OVG_REQUIRE(src && dst && F > 0 && h > 0 && w > 0 && H > 0 && W > 0 && C % 16 == 0, "bad arguments");
+  OVG_REQUIRE((tx == nullptr) == (ty == nullptr), "position tables come as a pair");
+  OVG_REQUIRE(F <= 65535 && H + 2 <= 65535, "grid too large");
+  ovg::UpsampleParams p{reinterpret_cast<const __nv_bfloat16*>(src), reinterpret_cast<__nv_bfloat16*>(dst), tx, ty,
+                        F, h, w, H, W, C,
+                        H > 1 ? static_cast<float>(h - 1) / static_cast<float>(H - 1) : 0.f,
+                        W > 1 ? static_cast<float>(w - 1) / static_cast<float>(W - 1) : 0.f};
+  const int per_row = (W + 2) * (C / 8);
+  dim3 grid((per_row + 255) / 256, H + 2, F);
+  ovg::upsample_bilinear_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
   return post_launch("ovg_upsample_bilinear");
 }
 

@@ -11,7 +11,7 @@ import torch
 
 from . import _lib as L
 from . import ops
-from .torch_parts import pack_injection, uv_posembed_table
+from .torch_parts import pack_injection, uv_posembed_separable, uv_posembed_table
 
 BF16, F32 = torch.bfloat16, torch.float32
 
@@ -170,6 +170,12 @@ class Engine:
         key = (C, h, w, round(aspect, 9))
         if key not in self._tables:
             self._tables[key] = uv_posembed_table(C, h, w, aspect, self.device)
+        return self._tables[key]
+
+    def table_xy(self, C: int, h: int, w: int, aspect: float):
+        key = ("xy", C, h, w, round(aspect, 9))
+        if key not in self._tables:
+            self._tables[key] = uv_posembed_separable(C, h, w, aspect, self.device)
         return self._tables[key]
 
     # ------------------------------------------------------------------------------------------ DINOv2 patchifier
@@ -344,13 +350,14 @@ class Engine:
                      gh=lh, gw=lw)
             th, tw = sizes[lvl - 1] if lvl > 0 else (2 * lh, 2 * lw)
             X = ws.get(f"dpt_x{lvl}", (Fc, th + 2, tw + 2, f))
-            ops.upsample_bilinear(Wv, X, None, Fc, lh, lw, th, tw, f)
+            ops.upsample_bilinear(Wv, X, None, None, Fc, lh, lw, th, tw, f)
         th, tw = 2 * sizes[0][0], 2 * sizes[0][1]
         o1 = ws.get("dpt_o1", (Fc, th + 2, tw + 2, f // 2))
         self.conv3x3(X, pk.oc1_w, pk.oc1_b, o1, Fc, th, tw)
         Hh, Ww = hp * self.patch, wp * self.patch
         up = ws.get("dpt_up", (Fc, Hh + 2, Ww + 2, f // 2))
-        ops.upsample_bilinear(o1, up, self.table(f // 2, Hh, Ww, aspect), Fc, th, tw, Hh, Ww, f // 2)
+        tx, ty = self.table_xy(f // 2, Hh, Ww, aspect)
+        ops.upsample_bilinear(o1, up, tx, ty, Fc, th, tw, Hh, Ww, f // 2)
         ops.gemm(up.reshape(-1, f // 2), pk.oc2_w, taps=_taps(Ww), epi=L.EPI_HEADTAIL, bias=pk.oc2_b, w2=pk.w2, b2=pk.b2,
                  outc=pk.outc, head_act=head_act, preds=preds[f0:f0 + Fc], conf=conf[f0:f0 + Fc], rowmap=L.ROWS_PAD,
                  gh=Hh, gw=Ww)

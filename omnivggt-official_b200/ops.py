@@ -129,5 +129,6 @@ def im2col3x3s2(src, dst, F, h, w, C):
     L.check(L.lib().ovg_im2col3x3s2(src.data_ptr(), dst.data_ptr(), F, h, w, C, L.stream()))
 
 
-def upsample_bilinear(src, dst, table, F, h, w, H, W, C):
-    L.check(L.lib().ovg_upsample_bilinear(src.data_ptr(), dst.data_ptr(), L.ptr(table), F, h, w, H, W, C, L.stream()))
+def upsample_bilinear(src, dst, tx, ty, F, h, w, H, W, C):
+    """tx [W, C/2], ty [H, C/2]: separable UV position embedding (or both None)."""
+    L.check(L.lib().ovg_upsample_bilinear(src.data_ptr(), dst.data_ptr(), L.ptr(tx), L.ptr(ty), F, h, w, H, W, C, L.stream()))

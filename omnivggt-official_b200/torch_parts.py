@@ -182,3 +182,20 @@ def uv_posembed_table(C: int, h: int, w: int, aspect: float, device) -> Tensor:
         return torch.cat([o.sin(), o.cos()], 1).float()
 
     return (torch.cat([sc(uu), sc(vv)], -1) * 0.1).contiguous().to(device)
+
+
+def uv_posembed_separable(C: int, h: int, w: int, aspect: float, device) -> Tuple[Tensor, Tensor]:
+    """The same embedding in separable form: channels [0, C/2) depend only on x, [C/2, C) only on y (heads/utils.py:26-30
+    concatenates emb_x and emb_y).  Returns (tx [w, C/2], ty [h, C/2]) fp32, x0.1."""
+    diag = (aspect ** 2 + 1.0) ** 0.5
+    sx, sy = aspect / diag, 1.0 / diag
+    xs = torch.linspace(-sx * (w - 1) / w, sx * (w - 1) / w, w, dtype=torch.float32)
+    ys = torch.linspace(-sy * (h - 1) / h, sy * (h - 1) / h, h, dtype=torch.float32)
+    q = C // 4
+    omega = 1.0 / (100.0 ** (torch.arange(q, dtype=torch.double) / q))
+
+    def sc(p):
+        o = p.double()[:, None] * omega[None]
+        return (torch.cat([o.sin(), o.cos()], 1).float() * 0.1).contiguous().to(device)
+
+    return sc(xs), sc(ys)

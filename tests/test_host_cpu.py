@@ -122,6 +122,9 @@ def test_uv_table_matches_oracle():
         t = TP.uv_posembed_table(C, h, w, a, "cpu")
         ref = O.uv_posembed(C, h, w, a).permute(1, 2, 0).reshape(h * w, C)
         assert torch.allclose(t, ref, atol=1e-6)
+        tx, ty = TP.uv_posembed_separable(C, h, w, a, "cpu")
+        sep = torch.cat([tx[None].expand(h, w, C // 2), ty[:, None].expand(h, w, C // 2)], -1).reshape(h * w, C)
+        assert torch.allclose(sep, ref, atol=1e-6)
 
 
 def test_dino_and_camera_head_match_oracle():

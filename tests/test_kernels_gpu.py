@@ -296,12 +296,13 @@ def test_upsample_bilinear(h, w, H, W, C):
     ops = _ops()
     Fr = 2
     x = randn(Fr, C, h, w, seed=1)
-    table = randn(H * W, C, seed=2)
+    tx, ty = randn(W, C // 2, seed=2), randn(H, C // 2, seed=3)
     xp = _to_pad(x)
     dst = torch.full((Fr, H + 2, W + 2, C), 3.0, device="cuda", dtype=BF16)
-    ops.upsample_bilinear(xp, dst, table, Fr, h, w, H, W, C)
+    ops.upsample_bilinear(xp, dst, tx, ty, Fr, h, w, H, W, C)
     ref = F.interpolate(xp[:, 1:-1, 1:-1].float().permute(0, 3, 1, 2), size=(H, W), mode="bilinear", align_corners=True)
-    ref = ref + table.reshape(H, W, C).permute(2, 0, 1)
+    table = torch.cat([tx[None, :, :].expand(H, W, C // 2), ty[:, None, :].expand(H, W, C // 2)], -1)
+    ref = ref + table.permute(2, 0, 1)
     assert rel(_from_pad(dst), ref) < 5e-3
     b = dst.clone()
     b[:, 1:-1, 1:-1] = 0
