@@ -241,62 +241,72 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
         const int kv_valid = min(128, p.n - j * 128);
         mbar_wait(&s_full[t], j & 1);
         tc_fence_after();
-        // ---- whole S row (128 fp32) into registers in one shot
-        uint32_t raw[128];
-        tmem_ld32(tS, raw);
-        tmem_ld32(tS + 32, raw + 32);
-        tmem_ld32(tS + 64, raw + 64);
-        tmem_ld32(tS + 96, raw + 96);
-        tmem_ld_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&s_taken[t]);   // S buffer free: the MMA warp may start S(j+1)
-        if (kv_valid != 128) {
-#pragma unroll
-          for (int i = 0; i < 128; ++i)
-            if (i >= kv_valid) raw[i] = 0xff800000u;   // -inf: excluded from the max, exp2 -> 0
-        }
-        float mx0 = -INFINITY, mx1 = -INFINITY;
-#pragma unroll
-        for (int i = 0; i < 128; i += 4) {
-          mx0 = fmaxf(fmaxf(mx0, __uint_as_float(raw[i])), __uint_as_float(raw[i + 1]));
-          mx1 = fmaxf(fmaxf(mx1, __uint_as_float(raw[i + 2])), __uint_as_float(raw[i + 3]));
-        }
-        const float m_new = fmaxf(m_used, fmaxf(mx0, mx1));
-        if (j == 0) {
-          m_used = m_new;
-        } else {
-          // PV(j-1) complete: O is stable (rescale below) and P(j-1) has been read (P buffer reusable)
+        if (j > 0) {   // PV(j-1) complete: O is stable (rebase below) and P(j-1) has been consumed (P buffer reusable)
           mbar_wait(&o_ready[t], (j - 1) & 1);
           tc_fence_after();
-          const bool need = (m_new - m_used) > 8.0f;
-          if (__any_sync(0xffffffffu, need)) {
-            const float alpha = need ? ex2_approx(m_used - m_new) : 1.0f;
-            if (need) {
-              m_used = m_new;
-              l *= alpha;
-            }
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-              uint32_t o[32];
-              tmem_ld32(tO + c * 32, o);
-              tmem_ld_wait();
-#pragma unroll
-              for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-              tmem_st32(tO + c * 32, o);
-            }
-            tmem_st_wait();
-          }
         }
-        // ---- P = exp2(S - m) (packed f32x2 subtract / accumulate), bf16 pack into the S columns
-        const float2 negm = make_float2(-m_used, -m_used);
+        // The S row is consumed in four 32-column chunks; the TMEM load of chunk c+1 is in flight while chunk c is
+        // exponentiated (a 128-column load costs ~570 clk per warp, measured: profiles/r01_tmem_mufu_microbench.txt).
+        // Probabilities are taken relative to the running reference m_used of the PREVIOUS chunks (exact: any
+        // reference cancels in O / l); only when a chunk exceeds it by more than 2^8 the row is re-based: l, O and
+        // the P chunks already written this step are rescaled (rare after the first tile).
         float2 acc = make_float2(0.f, 0.f);
+        uint32_t raw[2][32];
+        tmem_ld32(tS, raw[0]);
+        tmem_ld_wait();
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
+          uint32_t* cur = raw[c & 1];
+          if (c < 3) tmem_ld32(tS + (c + 1) * 32, raw[(c + 1) & 1]);
+          if (kv_valid != 128) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (c * 32 + i >= kv_valid) cur[i] = 0xff800000u;   // -inf: excluded from the max, exp2 -> 0
+          }
+          float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            mx0 = fmaxf(fmaxf(mx0, __uint_as_float(cur[i])), __uint_as_float(cur[i + 1]));
+            mx1 = fmaxf(fmaxf(mx1, __uint_as_float(cur[i + 2])), __uint_as_float(cur[i + 3]));
+          }
+          const float mxc = fmaxf(mx0, mx1);
+          const bool need = (mxc - m_used) > 8.0f;      // also true for the very first chunk (m_used = -inf)
+          if (__any_sync(0xffffffffu, need)) {
+            const float alpha = need ? ex2_approx(m_used - mxc) : 1.0f;   // 0 when m_used = -inf
+            if (need) m_used = mxc;
+            l *= alpha;
+            acc.x *= alpha;
+            acc.y *= alpha;
+            if (j > 0) {
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                uint32_t o[32];
+                tmem_ld32(tO + h * 32, o);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                tmem_st32(tO + h * 32, o);
+              }
+            }
+            if (c > 0) {
+              tmem_st_wait();   // P chunks of this step written so far must have landed before they are read back
+              for (int cc = 0; cc < c; ++cc) {
+                uint32_t q[16];
+                tmem_ld16(tP + cc * 16, q);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 16; ++i) q[i] = pack_bf16(bf16_lo(q[i]) * alpha, bf16_hi(q[i]) * alpha);
+                tmem_st16(tP + cc * 16, q);
+              }
+            }
+            tmem_st_wait();
+            // NB the tcgen05.wait::ld above also retired the in-flight load of chunk c+1: still correct, just not overlapped
+          }
+          const float2 negm = make_float2(-m_used, -m_used);
           uint32_t pk[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            float2 x = make_float2(__uint_as_float(raw[c * 32 + 2 * i]), __uint_as_float(raw[c * 32 + 2 * i + 1]));
+            float2 x = make_float2(__uint_as_float(cur[2 * i]), __uint_as_float(cur[2 * i + 1]));
             x = fadd2(x, negm);
             if (i >= 16 - OVG_ATT_EMU_PAIRS) {
               x = exp2_poly2(x);
@@ -308,6 +318,12 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
             pk[i] = pack_bf16(x.x, x.y);
           }
           tmem_st16(tP + c * 16, pk);
+          if (c < 3) tmem_ld_wait();
+          if (c == 2) {   // the whole S tile has left TMEM: the MMA warp may overwrite it with S(j+1)
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_taken[t]);
+          }
         }
         l += acc.x + acc.y;
         tmem_st_wait();
