@@ -183,45 +183,61 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
                   (j > 0 || k > 0) ? 1u : 0u);
         umma_commit(&o_ready[t]);
       };
+      // Issue schedule.  The two query tiles are kept HALF A STEP APART: while the softmax warps of one tile wait on
+      // their ~570-clk TMEM read the other tile's warps own the MUFU/FMA pipes.  (Issuing S_0,S_1 and PV_0,PV_1
+      // back to back puts both tiles in lock-step: loads coincide, the exp phases fight for the MUFU, and a KV step
+      // costs load + 2 x exp instead of load + exp -- measured 3300 vs ~1700 clk.)  Per KV step j:
+      //    A: S_0(j+1)   once tile 0 holds S_0(j) in registers           (s_taken[0])
+      //    B: PV_1(j-1)  once tile 1 has written P_1(j-1)                (p_full[1])
+      //    C: S_1(j+1)   once tile 1 holds S_1(j) in registers           (s_taken[1])
+      //    D: PV_0(j)    once tile 0 has written P_0(j)                  (p_full[0])
       mbar_wait(&q_full[0], 0);
       mbar_wait(&k_full[0], 0);
       tc_fence_after();
       issue_S(0, 0);
       if (two) {
         mbar_wait(&q_full[1], 0);
+        mbar_wait(&s_taken[0], 0);      // tile 1 starts when tile 0 has finished its first TMEM read
         tc_fence_after();
         issue_S(1, 0);
       }
       umma_commit(&k_empty[0]);
+      bool s0_taken0 = two;             // s_taken[0] phase 0 already consumed by the wait above
       for (int j = 0; j < nkv; ++j) {
         const int s = j % NS;
         const uint32_t ph = (j / NS) & 1;
         const int sn = (j + 1) % NS;
         const uint32_t phn = ((j + 1) / NS) & 1;
-        // S(j+1) as soon as the softmax warps hold S(j) in registers: it overlaps their exp/pack phase, so the next
-        // softmax step never waits for the tensor pipe.
-        if (j + 1 < nkv) {
+        const bool more = (j + 1) < nkv;
+        if (more) {                                                   // A
           mbar_wait(&k_full[sn], phn);
-          mbar_wait(&s_taken[0], j & 1);
+          if (!(j == 0 && s0_taken0)) mbar_wait(&s_taken[0], j & 1);
           tc_fence_after();
           issue_S(0, sn);
-          if (two) {
-            mbar_wait(&s_taken[1], j & 1);
-            tc_fence_after();
-            issue_S(1, sn);
-          }
-          umma_commit(&k_empty[sn]);
         }
-        mbar_wait(&v_full[s], ph);
+        if (two && j > 0) {                                           // B
+          mbar_wait(&p_full[1], (j - 1) & 1);
+          tc_fence_after();
+          issue_PV(1, (j - 1) % NS, j - 1);
+          umma_commit(&v_empty[(j - 1) % NS]);                        // V(j-1): PV_0(j-1) was issued one round earlier
+        }
+        if (two && more) {                                            // C
+          mbar_wait(&s_taken[1], j & 1);
+          tc_fence_after();
+          issue_S(1, sn);
+        }
+        if (more) umma_commit(&k_empty[sn]);
+        mbar_wait(&v_full[s], ph);                                    // D
         mbar_wait(&p_full[0], j & 1);
         tc_fence_after();
         issue_PV(0, s, j);
-        if (two) {
-          mbar_wait(&p_full[1], j & 1);
-          tc_fence_after();
-          issue_PV(1, s, j);
-        }
-        umma_commit(&v_empty[s]);
+        if (!two) umma_commit(&v_empty[s]);
+      }
+      if (two) {                                                      // trailing B
+        mbar_wait(&p_full[1], (nkv - 1) & 1);
+        tc_fence_after();
+        issue_PV(1, (nkv - 1) % NS, nkv - 1);
+        umma_commit(&v_empty[(nkv - 1) % NS]);
       }
     }
   } else if (warp >= 4) {
@@ -241,72 +257,62 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
         const int kv_valid = min(128, p.n - j * 128);
         mbar_wait(&s_full[t], j & 1);
         tc_fence_after();
-        if (j > 0) {   // PV(j-1) complete: O is stable (rebase below) and P(j-1) has been consumed (P buffer reusable)
+        // ---- whole S row (128 fp32) into registers in one shot
+        uint32_t raw[128];
+        tmem_ld32(tS, raw);
+        tmem_ld32(tS + 32, raw + 32);
+        tmem_ld32(tS + 64, raw + 64);
+        tmem_ld32(tS + 96, raw + 96);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_taken[t]);   // S buffer free: the MMA warp may start S(j+1)
+        if (kv_valid != 128) {
+#pragma unroll
+          for (int i = 0; i < 128; ++i)
+            if (i >= kv_valid) raw[i] = 0xff800000u;   // -inf: excluded from the max, exp2 -> 0
+        }
+        float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 128; i += 4) {
+          mx0 = fmaxf(fmaxf(mx0, __uint_as_float(raw[i])), __uint_as_float(raw[i + 1]));
+          mx1 = fmaxf(fmaxf(mx1, __uint_as_float(raw[i + 2])), __uint_as_float(raw[i + 3]));
+        }
+        const float m_new = fmaxf(m_used, fmaxf(mx0, mx1));
+        if (j == 0) {
+          m_used = m_new;
+        } else {
+          // PV(j-1) complete: O is stable (rescale below) and P(j-1) has been read (P buffer reusable)
           mbar_wait(&o_ready[t], (j - 1) & 1);
           tc_fence_after();
-        }
-        // The S row is consumed in four 32-column chunks; the TMEM load of chunk c+1 is in flight while chunk c is
-        // exponentiated (a 128-column load costs ~570 clk per warp, measured: profiles/r01_tmem_mufu_microbench.txt).
-        // Probabilities are taken relative to the running reference m_used of the PREVIOUS chunks (exact: any
-        // reference cancels in O / l); only when a chunk exceeds it by more than 2^8 the row is re-based: l, O and
-        // the P chunks already written this step are rescaled (rare after the first tile).
-        float2 acc = make_float2(0.f, 0.f);
-        uint32_t raw[2][32];
-        tmem_ld32(tS, raw[0]);
-        tmem_ld_wait();
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          uint32_t* cur = raw[c & 1];
-          if (c < 3) tmem_ld32(tS + (c + 1) * 32, raw[(c + 1) & 1]);
-          if (kv_valid != 128) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (c * 32 + i >= kv_valid) cur[i] = 0xff800000u;   // -inf: excluded from the max, exp2 -> 0
-          }
-          float mx0 = -INFINITY, mx1 = -INFINITY;
-#pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            mx0 = fmaxf(fmaxf(mx0, __uint_as_float(cur[i])), __uint_as_float(cur[i + 1]));
-            mx1 = fmaxf(fmaxf(mx1, __uint_as_float(cur[i + 2])), __uint_as_float(cur[i + 3]));
-          }
-          const float mxc = fmaxf(mx0, mx1);
-          const bool need = (mxc - m_used) > 8.0f;      // also true for the very first chunk (m_used = -inf)
+          const bool need = (m_new - m_used) > 8.0f;
           if (__any_sync(0xffffffffu, need)) {
-            const float alpha = need ? ex2_approx(m_used - mxc) : 1.0f;   // 0 when m_used = -inf
-            if (need) m_used = mxc;
-            l *= alpha;
-            acc.x *= alpha;
-            acc.y *= alpha;
-            if (j > 0) {
-#pragma unroll
-              for (int h = 0; h < 2; ++h) {
-                uint32_t o[32];
-                tmem_ld32(tO + h * 32, o);
-                tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-                tmem_st32(tO + h * 32, o);
-              }
+            const float alpha = need ? ex2_approx(m_used - m_new) : 1.0f;
+            if (need) {
+              m_used = m_new;
+              l *= alpha;
             }
-            if (c > 0) {
-              tmem_st_wait();   // P chunks of this step written so far must have landed before they are read back
-              for (int cc = 0; cc < c; ++cc) {
-                uint32_t q[16];
-                tmem_ld16(tP + cc * 16, q);
-                tmem_ld_wait();
 #pragma unroll
-                for (int i = 0; i < 16; ++i) q[i] = pack_bf16(bf16_lo(q[i]) * alpha, bf16_hi(q[i]) * alpha);
-                tmem_st16(tP + cc * 16, q);
-              }
+            for (int c = 0; c < 2; ++c) {
+              uint32_t o[32];
+              tmem_ld32(tO + c * 32, o);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+              tmem_st32(tO + c * 32, o);
             }
             tmem_st_wait();
-            // NB the tcgen05.wait::ld above also retired the in-flight load of chunk c+1: still correct, just not overlapped
           }
-          const float2 negm = make_float2(-m_used, -m_used);
+        }
+        // ---- P = exp2(S - m) (packed f32x2 subtract / accumulate), bf16 pack into the S columns
+        const float2 negm = make_float2(-m_used, -m_used);
+        float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
           uint32_t pk[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            float2 x = make_float2(__uint_as_float(cur[2 * i]), __uint_as_float(cur[2 * i + 1]));
+            float2 x = make_float2(__uint_as_float(raw[c * 32 + 2 * i]), __uint_as_float(raw[c * 32 + 2 * i + 1]));
             x = fadd2(x, negm);
             if (i >= 16 - OVG_ATT_EMU_PAIRS) {
               x = exp2_poly2(x);
@@ -318,12 +324,6 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
             pk[i] = pack_bf16(x.x, x.y);
           }
           tmem_st16(tP + c * 16, pk);
-          if (c < 3) tmem_ld_wait();
-          if (c == 2) {   // the whole S tile has left TMEM: the MMA warp may overwrite it with S(j+1)
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&s_taken[t]);
-          }
         }
         l += acc.x + acc.y;
         tmem_st_wait();

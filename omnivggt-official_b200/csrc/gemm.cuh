@@ -38,6 +38,7 @@ struct GemmParams {
   // ---- EPI_RESID:  out(fp32)[row,n] += gamma[n] * (acc + bias[n]),  row = row_index ? row_index[m] : m
   const float* gamma;
   const int* row_index;
+  int staged;  // 1: epilogue output goes through smem + TMA (store for EPI_BF16, fp32 reduce-add for EPI_RESID)
   // ---- EPI_QKV (layers/attention.py:52-58 fused: bias, q/k LayerNorm(64), 2-D RoPE, head-major bf16)
   __nv_bfloat16* q_out;
   __nv_bfloat16* k_out;
@@ -97,7 +98,8 @@ __device__ __forceinline__ float gelu_erf(float x) {
 // quarter of the accumulator stage, `m` is this thread's global row, `colhalf` selects which column chunks this warp owns.
 template <int BN, int EPI>
 __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const uint32_t trow, const int m, const int n0,
-                                              const int colhalf, const float* s_rope) {
+                                              const int colhalf, const float* s_rope, uint8_t* stg = nullptr,
+                                              const CUtensorMap* tmO = nullptr) {
   if constexpr (EPI == EPI_QKV) {
     // ---- per-row RoPE position (reference omnivggt_aggregator.py:215-224; layers/rope.py:39-59)
     int py = 0, px = 0;
@@ -223,12 +225,38 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const uint32_
       uint32_t raw[32];
       tmem_ld32(trow + c * 32, raw);
       tmem_ld_wait();
-      if (!(row_ok && n < p.N)) continue;
+      if (n >= p.N) continue;                       // warp-uniform
+      if (!p.staged && !row_ok) continue;           // staged: all lanes take part (TMA clips rows >= M)
       float v[32];
 #pragma unroll
       for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
 
       if constexpr (EPI == EPI_RESID) {
+        if (p.staged) {
+          // gamma * (acc + bias) -> swizzled fp32 smem tile [32 rows x 32 cols] of this warp -> TMA reduce-add into x.
+          // The SM never reads x: the read-modify-write happens in L2, and the stores leave as whole 128 B rows.
+          const int lane = threadIdx.x & 31;
+          if (lane == 0) tma_store_wait_read0();      // previous chunk's bulk read of this buffer has finished
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 g = __ldg(reinterpret_cast<const float4*>(p.gamma + n) + i);
+            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n) + i);
+            float4 o;
+            o.x = g.x * (v[4 * i + 0] + b.x);
+            o.y = g.y * (v[4 * i + 1] + b.y);
+            o.z = g.z * (v[4 * i + 2] + b.z);
+            o.w = g.w * (v[4 * i + 3] + b.w);
+            *reinterpret_cast<float4*>(stg + lane * 128 + ((i ^ (lane & 7)) << 4)) = o;
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tma_reduce_add_2d(tmO, stg, n, m - lane);
+            tma_store_commit();
+          }
+          continue;
+        }
         float* x = reinterpret_cast<float*>(p.out) + drow * p.ldo + n;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -278,7 +306,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const uint32_
           for (int i = 0; i < 32; ++i) v[i] += __ldg(t + i);
         }
         const long long off = drow * p.ldo + dcol;
-        if (p.skip1) {
+        if (p.skip1 && row_ok) {
           const uint4* s4 = reinterpret_cast<const uint4*>(p.skip1 + off);
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
@@ -289,7 +317,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const uint32_
             v[8 * i + 6] += bf16_lo(sv.w); v[8 * i + 7] += bf16_hi(sv.w);
           }
         }
-        if (p.skip2) {
+        if (p.skip2 && row_ok) {
           const uint4* s4 = reinterpret_cast<const uint4*>(p.skip2 + off);
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
@@ -310,6 +338,27 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const uint32_
         if (!interior) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = 0.f;
+        }
+        if (p.staged) {
+          const int lane = threadIdx.x & 31;
+          if (lane == 0) tma_store_wait_read0();
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            uint4 o;
+            o.x = pack_bf16(v[8 * i + 0], v[8 * i + 1]);
+            o.y = pack_bf16(v[8 * i + 2], v[8 * i + 3]);
+            o.z = pack_bf16(v[8 * i + 4], v[8 * i + 5]);
+            o.w = pack_bf16(v[8 * i + 6], v[8 * i + 7]);
+            *reinterpret_cast<uint4*>(stg + lane * 64 + ((i ^ ((lane >> 1) & 3)) << 4)) = o;   // 64B-swizzled tile
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(tmO, stg, n, m - lane);
+            tma_store_commit();
+          }
+          continue;
         }
         uint4* d4 = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + off);
 #pragma unroll
@@ -474,17 +523,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 // 128 x 256 single-CTA tile needs ~87 FLOP per L2->SM byte and saturates the L2 fabric (~10-12 TB/s) near 1 PFLOP/s;
 // the paired tile needs 131 FLOP/B.  The pair leader issues M=256 MMAs that write both CTAs' TMEM; every CTA runs its own
 // TMA producer and epilogue (rows [128*rank, 128*rank+128) of the tile).
+constexpr int GEMM2_STG_BYTES = 8 * 4096;   // one 32 x 32 fp32 (or bf16) staging tile per epilogue warp; aliases the rope table
 template <int BN>
 struct Gemm2Cfg {
-  static constexpr int STAGES = BN >= 256 ? 6 : 8;
+  static constexpr int STAGES = BN >= 256 ? 5 : 7;
   static constexpr int B_BYTES = (BN / 2) * GEMM_BK * 2;       // each CTA stages half of the B rows
   static constexpr int STAGE_BYTES = GEMM_A_BYTES + B_BYTES;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + 2 * 64 * 17 * 4;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + 1024 + GEMM2_STG_BYTES;
 };
 
 template <int BN, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
-gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+             const __grid_constant__ CUtensorMap tmO, const GemmParams p) {
   using Cfg2 = Gemm2Cfg<BN>;
   constexpr int STAGES = Cfg2::STAGES;
   constexpr int GEMM2_B_BYTES = Cfg2::B_BYTES;
@@ -499,7 +550,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   uint64_t* tfull = bars + 2 * STAGES;      // per CTA: multicast MMA commit
   uint64_t* tempty = bars + 2 * STAGES + 2; // used in the leader only: 8 epilogue warps x 2 CTAs
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
-  float* s_rope = reinterpret_cast<float*>(smem + STAGES * GEMM2_STAGE_BYTES + 256);
+  uint8_t* s_stage = smem + STAGES * GEMM2_STAGE_BYTES + 1024;     // 1024-aligned: swizzled TMA-store tiles
+  float* s_rope = reinterpret_cast<float*>(s_stage);                // QKV epilogue only (never staged)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -514,6 +566,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (p.staged) tma_prefetch_desc(&tmO);
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], 1);
@@ -611,7 +664,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       mbar_wait(&tfull[as], aph);
       tc_fence_after();
       const uint32_t trow = tmem_base + as * BN + (static_cast<uint32_t>(quarter * 32) << 16);
-      epilogue_tile<BN, EPI>(p, trow, m, n0, colhalf, s_rope);
+      epilogue_tile<BN, EPI>(p, trow, m, n0, colhalf, s_rope, s_stage + (warp - 2) * 4096, &tmO);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -624,6 +677,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       }
     }
   }
+  if (p.staged && warp >= 2 && lane == 0) tma_store_wait_all();   // bulk stores issued by this thread have completed
   tc_fence_before();
   cluster_sync();   // the peer may still signal barriers / read smem of this CTA until both are done
   if (warp == 1) {

@@ -16,6 +16,7 @@ namespace {
 
 thread_local std::string g_err;
 std::atomic<long long> g_launches{0};
+const bool g_stage_default = [] { const char* e = getenv("OVG_GEMM_STAGE"); return !(e && e[0] == '0'); }();   // A/B switch
 const bool g_pair_default = [] { const char* e = getenv("OVG_GEMM_PAIR"); return !(e && e[0] == '0'); }();   // A/B switch
 
 int fail(int code, const std::string& msg) {
@@ -55,7 +56,7 @@ PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
 
 struct MapKey {
   const void* ptr;
-  unsigned long long d0, d1, d2, ld, box1;
+  unsigned long long d0, d1, d2, ld, box1;   // box1 also carries (kind << 32) for output maps
   bool operator==(const MapKey& o) const {
     return ptr == o.ptr && d0 == o.d0 && d1 == o.d1 && d2 == o.d2 && ld == o.ld && box1 == o.box1;
   }
@@ -105,6 +106,42 @@ int get_map(const void* ptr, unsigned long long d0, unsigned long long d1, unsig
   return OVG_OK;
 }
 
+// Output map for the staged epilogue: [rows, cols] row-major (row stride ld elements), box 32 cols x 32 rows;
+// bf16 -> 64 B inner box, SWIZZLE_64B; fp32 -> 128 B inner box, SWIZZLE_128B.
+int get_out_map(const void* ptr, bool f32, unsigned long long cols, unsigned long long rows, unsigned long long ld,
+                CUtensorMap* out) {
+  MapKey key{ptr, cols, rows, 0, ld, (f32 ? 2ull : 1ull) << 32};
+  {
+    std::lock_guard<std::mutex> g(g_map_mu);
+    auto it = g_maps.find(key);
+    if (it != g_maps.end()) {
+      *out = it->second;
+      return OVG_OK;
+    }
+  }
+  auto enc = get_encode();
+  if (!enc) return fail(OVG_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  const unsigned esz = f32 ? 4 : 2;
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || ((ld * esz) & 15))
+    return fail(OVG_E_INVALID, "TMA store target must be 16-byte aligned with a 16-byte multiple row stride");
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstr[1] = {ld * esz};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUtensorMap m;
+  CUresult r = enc(&m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr),
+                   gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   f32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(OVG_E_CUDA, "cuTensorMapEncodeTiled(out) failed (" + std::to_string(int(r)) + ")");
+  {
+    std::lock_guard<std::mutex> g(g_map_mu);
+    g_maps.emplace(key, m);
+  }
+  *out = m;
+  return OVG_OK;
+}
+
 int num_sms() {
   static int n = [] {
     int dev = 0, v = 0;
@@ -131,7 +168,8 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const ovg::GemmPar
 }
 
 template <int BN, int EPI>
-int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const ovg::GemmParams& p, cudaStream_t st) {
+int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const ovg::GemmParams& p,
+                 cudaStream_t st) {
   using Cfg = ovg::Gemm2Cfg<BN>;
   static bool attr_set = false;
   auto kern = ovg::gemm2_kernel<BN, EPI>;
@@ -142,7 +180,7 @@ int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const ovg::GemmPa
   const int tiles = ((p.M + 255) / 256) * ((p.N + BN - 1) / BN);
   const int pairs = num_sms() / 2;
   const int grid = 2 * (tiles < pairs ? tiles : pairs);
-  kern<<<grid, ovg::GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, p);
+  kern<<<grid, ovg::GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, to, p);
   return post_launch("ovg_gemm(2sm)");
 }
 
@@ -280,18 +318,28 @@ int ovg_gemm(const ovg_gemm_args* a, void* stream) {
     const int pbn = (a->block_n == 384 || (a->block_n == 0 && a->n < 256)) ? 128 : 256;
     rc = get_map(a->b, ktot, a->n, 0, a->ldb, pbn / 2, &tb);
     if (rc) return rc;
+    // staged epilogue (smem -> TMA store / fp32 reduce-add) whenever output rows are the GEMM rows
+    CUtensorMap to = ta;
+    const bool stage_ok = g_stage_default &&
+                          ((a->epi == OVG_EPI_RESID && !a->row_index) ||
+                           (a->epi == OVG_EPI_BF16 && (a->rowmap == OVG_ROWS_IDENT || a->rowmap == OVG_ROWS_PAD)));
+    if (stage_ok) {
+      rc = get_out_map(a->out, a->epi == OVG_EPI_RESID, a->n, a->m, a->ldo, &to);
+      if (rc) return rc;
+      p.staged = 1;
+    }
     if (pbn == 256) {
       switch (a->epi) {
-        case OVG_EPI_BF16: return launch_gemm2<256, ovg::EPI_BF16>(ta, tb, p, st);
-        case OVG_EPI_RESID: return launch_gemm2<256, ovg::EPI_RESID>(ta, tb, p, st);
-        case OVG_EPI_QKV: return launch_gemm2<256, ovg::EPI_QKV>(ta, tb, p, st);
+        case OVG_EPI_BF16: return launch_gemm2<256, ovg::EPI_BF16>(ta, tb, to, p, st);
+        case OVG_EPI_RESID: return launch_gemm2<256, ovg::EPI_RESID>(ta, tb, to, p, st);
+        case OVG_EPI_QKV: return launch_gemm2<256, ovg::EPI_QKV>(ta, tb, to, p, st);
         default: return fail(OVG_E_INVALID, "ovg_gemm: unknown epilogue");
       }
     }
     switch (a->epi) {
-      case OVG_EPI_BF16: return launch_gemm2<128, ovg::EPI_BF16>(ta, tb, p, st);
-      case OVG_EPI_RESID: return launch_gemm2<128, ovg::EPI_RESID>(ta, tb, p, st);
-      case OVG_EPI_QKV: return launch_gemm2<128, ovg::EPI_QKV>(ta, tb, p, st);
+      case OVG_EPI_BF16: return launch_gemm2<128, ovg::EPI_BF16>(ta, tb, to, p, st);
+      case OVG_EPI_RESID: return launch_gemm2<128, ovg::EPI_RESID>(ta, tb, to, p, st);
+      case OVG_EPI_QKV: return launch_gemm2<128, ovg::EPI_QKV>(ta, tb, to, p, st);
       default: return fail(OVG_E_INVALID, "ovg_gemm: unknown epilogue");
     }
   }
