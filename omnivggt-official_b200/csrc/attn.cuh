@@ -26,7 +26,15 @@ struct AttnParams {
   int heads;
   int C;        // heads * 64 (row stride of `out`)
   __nv_bfloat16* out;  // [batch, n, C]
+  long long* prof;     // optional [2][8] cycle counters (OVG_ATT_PROFILE builds only)
 };
+#ifdef OVG_ATT_PROFILE
+#define ATT_T(var) const long long var = clock64()
+#define ATT_ACC(slot, a, b) do { if (prof_on) prof_acc[slot] += (b) - (a); } while (0)
+#else
+#define ATT_T(var)
+#define ATT_ACC(slot, a, b)
+#endif
 
 constexpr int ATT_THREADS = 384;
 constexpr int ATT_KV_STAGES = 4;
@@ -183,61 +191,45 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
                   (j > 0 || k > 0) ? 1u : 0u);
         umma_commit(&o_ready[t]);
       };
-      // Issue schedule.  The two query tiles are kept HALF A STEP APART: while the softmax warps of one tile wait on
-      // their ~570-clk TMEM read the other tile's warps own the MUFU/FMA pipes.  (Issuing S_0,S_1 and PV_0,PV_1
-      // back to back puts both tiles in lock-step: loads coincide, the exp phases fight for the MUFU, and a KV step
-      // costs load + 2 x exp instead of load + exp -- measured 3300 vs ~1700 clk.)  Per KV step j:
-      //    A: S_0(j+1)   once tile 0 holds S_0(j) in registers           (s_taken[0])
-      //    B: PV_1(j-1)  once tile 1 has written P_1(j-1)                (p_full[1])
-      //    C: S_1(j+1)   once tile 1 holds S_1(j) in registers           (s_taken[1])
-      //    D: PV_0(j)    once tile 0 has written P_0(j)                  (p_full[0])
       mbar_wait(&q_full[0], 0);
       mbar_wait(&k_full[0], 0);
       tc_fence_after();
       issue_S(0, 0);
       if (two) {
         mbar_wait(&q_full[1], 0);
-        mbar_wait(&s_taken[0], 0);      // tile 1 starts when tile 0 has finished its first TMEM read
         tc_fence_after();
         issue_S(1, 0);
       }
       umma_commit(&k_empty[0]);
-      bool s0_taken0 = two;             // s_taken[0] phase 0 already consumed by the wait above
       for (int j = 0; j < nkv; ++j) {
         const int s = j % NS;
         const uint32_t ph = (j / NS) & 1;
         const int sn = (j + 1) % NS;
         const uint32_t phn = ((j + 1) / NS) & 1;
-        const bool more = (j + 1) < nkv;
-        if (more) {                                                   // A
+        // S(j+1) as soon as the softmax warps hold S(j) in registers: it overlaps their exp/pack phase, so the next
+        // softmax step never waits for the tensor pipe.
+        if (j + 1 < nkv) {
           mbar_wait(&k_full[sn], phn);
-          if (!(j == 0 && s0_taken0)) mbar_wait(&s_taken[0], j & 1);
+          mbar_wait(&s_taken[0], j & 1);
           tc_fence_after();
           issue_S(0, sn);
+          if (two) {
+            mbar_wait(&s_taken[1], j & 1);
+            tc_fence_after();
+            issue_S(1, sn);
+          }
+          umma_commit(&k_empty[sn]);
         }
-        if (two && j > 0) {                                           // B
-          mbar_wait(&p_full[1], (j - 1) & 1);
-          tc_fence_after();
-          issue_PV(1, (j - 1) % NS, j - 1);
-          umma_commit(&v_empty[(j - 1) % NS]);                        // V(j-1): PV_0(j-1) was issued one round earlier
-        }
-        if (two && more) {                                            // C
-          mbar_wait(&s_taken[1], j & 1);
-          tc_fence_after();
-          issue_S(1, sn);
-        }
-        if (more) umma_commit(&k_empty[sn]);
-        mbar_wait(&v_full[s], ph);                                    // D
+        mbar_wait(&v_full[s], ph);
         mbar_wait(&p_full[0], j & 1);
         tc_fence_after();
         issue_PV(0, s, j);
-        if (!two) umma_commit(&v_empty[s]);
-      }
-      if (two) {                                                      // trailing B
-        mbar_wait(&p_full[1], (nkv - 1) & 1);
-        tc_fence_after();
-        issue_PV(1, (nkv - 1) % NS, nkv - 1);
-        umma_commit(&v_empty[(nkv - 1) % NS]);
+        if (two) {
+          mbar_wait(&p_full[1], j & 1);
+          tc_fence_after();
+          issue_PV(1, s, j);
+        }
+        umma_commit(&v_empty[s]);
       }
     }
   } else if (warp >= 4) {
@@ -253,10 +245,16 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
       const uint32_t tO = tmem_base + 384 + t * 64 + lane_off;
       float m_used = -INFINITY;
       float l = 0.f;
+#ifdef OVG_ATT_PROFILE
+      const bool prof_on = p.prof && blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0 && (warp & 3) == 0 && lane == 0;
+      long long prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#endif
       for (int j = 0; j < nkv; ++j) {
         const int kv_valid = min(128, p.n - j * 128);
+        ATT_T(t_a);
         mbar_wait(&s_full[t], j & 1);
         tc_fence_after();
+        ATT_T(t_b);
         // ---- whole S row (128 fp32) into registers in one shot
         uint32_t raw[128];
         tmem_ld32(tS, raw);
@@ -264,6 +262,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
         tmem_ld32(tS + 64, raw + 64);
         tmem_ld32(tS + 96, raw + 96);
         tmem_ld_wait();
+        ATT_T(t_c);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&s_taken[t]);   // S buffer free: the MMA warp may start S(j+1)
@@ -283,8 +282,11 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
           m_used = m_new;
         } else {
           // PV(j-1) complete: O is stable (rescale below) and P(j-1) has been read (P buffer reusable)
+          ATT_T(t_d);
           mbar_wait(&o_ready[t], (j - 1) & 1);
           tc_fence_after();
+          ATT_T(t_e);
+          ATT_ACC(2, t_d, t_e);
           const bool need = (m_new - m_used) > 8.0f;
           if (__any_sync(0xffffffffu, need)) {
             const float alpha = need ? ex2_approx(m_used - m_new) : 1.0f;
@@ -326,11 +328,24 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
           tmem_st16(tP + c * 16, pk);
         }
         l += acc.x + acc.y;
+        ATT_T(t_f);
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[t]);
+        ATT_T(t_g);
+        ATT_ACC(0, t_a, t_b);   // wait for S
+        ATT_ACC(1, t_b, t_c);   // TMEM read of the S row
+        ATT_ACC(3, t_c, t_f);   // max + (o_ready wait) + exp + P store issue
+        ATT_ACC(4, t_f, t_g);   // wait::st + fence + arrive
+        ATT_ACC(5, t_a, t_g);   // whole step
       }
+#ifdef OVG_ATT_PROFILE
+      if (prof_on) {
+        for (int i = 0; i < 8; ++i) p.prof[t * 8 + i] = prof_acc[i];
+        p.prof[t * 8 + 7] = nkv;
+      }
+#endif
       // ---- epilogue: O / l -> bf16 -> out[b, qrow, head*64 .. +64)
       mbar_wait(&o_ready[t], (nkv - 1) & 1);
       tc_fence_after();

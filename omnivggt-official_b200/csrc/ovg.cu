@@ -196,7 +196,11 @@ int dispatch_bn(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const ovg:
 
 }  // namespace
 
+long long* g_attn_prof = nullptr;   // set through ovg_debug_set_attn_profile (profiling builds)
+
 extern "C" {
+
+void ovg_debug_set_attn_profile(long long* buf) { g_attn_prof = buf; }
 
 int ovg_version(void) { return 1; }
 const char* ovg_last_error(void) { return g_err.c_str(); }
@@ -372,7 +376,7 @@ int ovg_attention(const void* q, const void* k, const void* v, void* out, int ba
     OVG_CUDA(cudaFuncSetAttribute(ovg::attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ovg::ATT_SMEM_BYTES));
     attr_set = true;
   }
-  ovg::AttnParams p{n, heads, heads * 64, reinterpret_cast<__nv_bfloat16*>(out)};
+  ovg::AttnParams p{n, heads, heads * 64, reinterpret_cast<__nv_bfloat16*>(out), g_attn_prof};
   dim3 grid((n + 255) / 256, heads, batch);
   ovg::attn_kernel<<<grid, ovg::ATT_THREADS, ovg::ATT_SMEM_BYTES, st>>>(tq, tk, tv, p);
   return post_launch("ovg_attention");
