@@ -6,7 +6,7 @@
 //
 // CTA = 256 query rows (two 128-row tiles, ping-pong) of one (batch, head).  Roles:
 //   warp 0        TMA producer: Q tiles once, K/V tiles through a 4-stage ring
-//   warp 1        MMA issuer:   S_t = Q_t K^T (SS, M128 N128 K64) and O_t += P_t V (TS: P read from TMEM,
+//   warps 1,2     MMA issuers (one per query tile): S_t = Q_t K^T (SS, M128 N128 K64) and O_t += P_t V (TS: P from TMEM,
 //                               V as MN-major smem operand, M128 N64 K128); issue order S_t(j+1), PV_t(j)
 //   warps 4-7     softmax for tile 0 (one query row per thread; row = TMEM lane; the whole 128-wide S row is
 //                 held in registers: one TMEM read per element; setmaxnreg moves registers from warps 0-3 here)
@@ -129,9 +129,9 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
     }
     for (int i = 0; i < NS; ++i) {
       mbar_init(&k_full[i], 1);
-      mbar_init(&k_empty[i], 1);
+      mbar_init(&k_empty[i], two ? 2 : 1);   // one commit per MMA issuer (tile)
       mbar_init(&v_full[i], 1);
-      mbar_init(&v_empty[i], 1);
+      mbar_init(&v_empty[i], two ? 2 : 1);
     }
     fence_barrier_init();
   }
@@ -169,66 +169,57 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
         }
       }
     }
-  } else if (warp == 1) {
-    if (lane == 0) {
+  } else if (warp == 1 || warp == 2) {
+    // One MMA issuer per query tile (warp 1: tile 0, warp 2: tile 1).  With a single issuer the two tiles were coupled by
+    // head-of-line blocking on its in-order barrier waits (PV_t was issued ~800 clk after P_t was ready and the tiles ran
+    // in lock-step, both exp phases fighting for the MUFU at the same time).  Independent issuers let each tile run at
+    // its own pace; tile 1 is started half a step late so that one tile's waits fall into the other tile's exp phase.
+    const int t = warp - 1;
+    if (lane == 0 && (t == 0 || two)) {
       constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
       constexpr uint32_t idesc_pv = make_idesc_bf16(128, 64, 0, 1);  // B (=V) is MN-major
-      const uint32_t tS[2] = {tmem_base, tmem_base + 128};
-      const uint32_t tP[2] = {tmem_base + 256, tmem_base + 320};
-      const uint32_t tO[2] = {tmem_base + 384, tmem_base + 448};
-      auto issue_S = [&](int t, int stage) {
-        const uint64_t adesc = make_sw128_desc(smem_u32(sQ + t * ATT_TILE_BYTES));
-        const uint64_t bdesc = make_sw128_desc(smem_u32(sK + stage * ATT_TILE_BYTES));
+      const uint32_t tS = tmem_base + t * 128;
+      const uint32_t tP = tmem_base + 256 + t * 64;
+      const uint32_t tO = tmem_base + 384 + t * 64;
+      const uint64_t qdesc = make_sw128_desc(smem_u32(sQ + t * ATT_TILE_BYTES));
+      const uint64_t kdesc0 = make_sw128_desc(smem_u32(sK));
+      const uint64_t vdesc0 = make_sw128_desc(smem_u32(sV));
+      constexpr uint64_t kStageStep = ATT_TILE_BYTES >> 4;     // descriptor address units are 16 B
+      auto issue_S = [&](int stage) {
+        const uint64_t bdesc = kdesc0 + stage * kStageStep;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_ss(tS[t], adesc + 2 * k, bdesc + 2 * k, idesc_s, k > 0 ? 1u : 0u);
+        for (int k = 0; k < 4; ++k) umma_ss(tS, qdesc + 2 * k, bdesc + 2 * k, idesc_s, k > 0 ? 1u : 0u);
         umma_commit(&s_full[t]);
       };
-      auto issue_PV = [&](int t, int stage, int j) {
-        const uint64_t bdesc = make_sw128_desc(smem_u32(sV + stage * ATT_TILE_BYTES));
+      auto issue_PV = [&](int stage, int j) {
+        const uint64_t bdesc = vdesc0 + stage * kStageStep;
 #pragma unroll
         for (int k = 0; k < 8; ++k)   // 16 keys per MMA: P advances 8 cols (bf16x2), V advances 16 rows = 2048 B
-          umma_ts(tO[t], tP[t] + 8 * k, bdesc + static_cast<uint64_t>(k) * (2048 >> 4), idesc_pv,
-                  (j > 0 || k > 0) ? 1u : 0u);
+          umma_ts(tO, tP + 8 * k, bdesc + static_cast<uint64_t>(k) * (2048 >> 4), idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
         umma_commit(&o_ready[t]);
       };
-      mbar_wait(&q_full[0], 0);
+      mbar_wait(&q_full[t], 0);
       mbar_wait(&k_full[0], 0);
+      if (t == 1) __nanosleep(450);     // ~half a KV step
       tc_fence_after();
-      issue_S(0, 0);
-      if (two) {
-        mbar_wait(&q_full[1], 0);
-        tc_fence_after();
-        issue_S(1, 0);
-      }
+      issue_S(0);
       umma_commit(&k_empty[0]);
       for (int j = 0; j < nkv; ++j) {
         const int s = j % NS;
         const uint32_t ph = (j / NS) & 1;
         const int sn = (j + 1) % NS;
         const uint32_t phn = ((j + 1) / NS) & 1;
-        // S(j+1) as soon as the softmax warps hold S(j) in registers: it overlaps their exp/pack phase, so the next
-        // softmax step never waits for the tensor pipe.
-        if (j + 1 < nkv) {
+        if (j + 1 < nkv) {              // S(j+1) as soon as the softmax warps hold S(j) in registers
           mbar_wait(&k_full[sn], phn);
-          mbar_wait(&s_taken[0], j & 1);
+          mbar_wait(&s_taken[t], j & 1);
           tc_fence_after();
-          issue_S(0, sn);
-          if (two) {
-            mbar_wait(&s_taken[1], j & 1);
-            tc_fence_after();
-            issue_S(1, sn);
-          }
+          issue_S(sn);
           umma_commit(&k_empty[sn]);
         }
         mbar_wait(&v_full[s], ph);
-        mbar_wait(&p_full[0], j & 1);
+        mbar_wait(&p_full[t], j & 1);
         tc_fence_after();
-        issue_PV(0, s, j);
-        if (two) {
-          mbar_wait(&p_full[1], j & 1);
-          tc_fence_after();
-          issue_PV(1, s, j);
-        }
+        issue_PV(s, j);
         umma_commit(&v_empty[s]);
       }
     }

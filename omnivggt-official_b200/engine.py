@@ -91,6 +91,7 @@ class Workspace:
     def __init__(self, device):
         self.device = device
         self.bufs: Dict[str, torch.Tensor] = {}
+        self.version = 0          # bumped on every (re)allocation: captured CUDA graphs hold raw pointers
 
     def get(self, name: str, shape: Sequence[int], dtype=BF16, zero: bool = False) -> torch.Tensor:
         n = 1
@@ -101,6 +102,7 @@ class Workspace:
         if buf is None or buf.dtype != dtype or buf.numel() < n:
             buf = torch.empty(max(n, 1), device=self.device, dtype=dtype)
             self.bufs[key] = buf
+            self.version += 1
         v = buf[:n].view(*shape)
         if zero:
             v.zero_()

@@ -11,6 +11,8 @@ construction, and extra keyword arguments select reduced architectures for tests
 """
 from __future__ import annotations
 
+import os
+import warnings
 from typing import Dict, List, Optional, Sequence
 
 import torch
@@ -36,13 +38,16 @@ class OmniVGGT(nn.Module, PyTorchModelHubMixin):
                  dpt_out_channels: Sequence[int] = (256, 512, 1024, 1024),
                  dpt_layers: Sequence[int] = (4, 11, 17, 23), camera_heads: int = 16, camera_trunk_depth: int = 4,
                  dino_backend: str = "ovg", dino_dtype: torch.dtype = torch.bfloat16, camera_dtype: torch.dtype = torch.bfloat16,
-                 init_seed: Optional[int] = 0):
+                 use_cuda_graph: Optional[bool] = None, init_seed: Optional[int] = 0):
         super().__init__()
         self.img_size, self.patch_size, self.embed_dim = img_size, patch_size, embed_dim
         self.dpt_layers = tuple(dpt_layers)
         self.dino_backend = dino_backend   # "ovg": frozen patchifier on the libovg kernels; "torch": library kernels
         self.dino_dtype = dino_dtype
         self.camera_dtype = camera_dtype     # precision of the camera-head weight matrices (fp32 selectable)
+        # replay the ~1000 kernel launches of a forward from a CUDA graph once a shape has been seen twice
+        self.use_cuda_graph = (os.environ.get("OVG_CUDA_GRAPH", "1") != "0") if use_cuda_graph is None else use_cuda_graph
+        self._graphs = {}
         pe = "conv" if "conv" in patch_embed else "dino"
         self.aggregator = AggregatorParams(img_size, patch_size, embed_dim, depth, 64, num_register_tokens, pe,
                                            dino_depth, dino_heads)
@@ -65,6 +70,7 @@ class OmniVGGT(nn.Module, PyTorchModelHubMixin):
 
     def _invalidate(self):
         self._engine = None
+        self._graphs = {}
         object.__setattr__(self, "_dino_lp", None)
         TP.clear_lp_cache(self)
 
@@ -120,6 +126,57 @@ class OmniVGGT(nn.Module, PyTorchModelHubMixin):
         if len(cam_idx):
             assert extrinsics is not None and intrinsics is not None, "camera_gt_index given without cameras"
         eng = self.engine()
+        args = (images, extrinsics, intrinsics, depth, mask, depth_idx, cam_idx)
+        if self.use_cuda_graph and images.is_cuda and not torch.cuda.is_current_stream_capturing():
+            return self._forward_graphed(eng, *args)
+        return self._forward_impl(eng, *args)
+
+    # ---------------------------------------------------------------------------------------------- CUDA graph replay
+    def _forward_graphed(self, eng, images, extrinsics, intrinsics, depth, mask, depth_idx, cam_idx):
+        """Same computation, launched from a captured CUDA graph (a forward is >1000 kernel launches; issuing them from
+        Python costs about as much host time as the GPU needs to run them).  A graph is captured the third time a
+        (shape, index-list) signature is seen; inputs are copied into static buffers, outputs are cloned."""
+        need_c, need_d = len(cam_idx) > 0, len(depth_idx) > 0
+        key = (tuple(images.shape), images.dtype, tuple(depth_idx), tuple(cam_idx))
+        ent = self._graphs.get(key)
+        if ent is None:
+            ent = self._graphs[key] = {"calls": 0, "graph": None}
+        ent["calls"] += 1
+        if ent["graph"] is None and (ent["calls"] < 3 or ent.get("failed")):
+            return self._forward_impl(eng, images, extrinsics, intrinsics, depth, mask, depth_idx, cam_idx)
+        dyn = [images, extrinsics if need_c else None, intrinsics if need_c else None, depth if need_d else None,
+               mask if need_d else None]
+        if ent["graph"] is None or ent["ws_version"] != eng.ws.version:
+            try:
+                static = [None if t is None else t.detach().clone() for t in dyn]
+                s = torch.cuda.Stream()
+                s.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(s):      # allocator warm-up on a side stream, as the capture API requires
+                    self._forward_impl(eng, *static, depth_idx, cam_idx)
+                torch.cuda.current_stream().wait_stream(s)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    out = self._forward_impl(eng, *static, depth_idx, cam_idx)
+                ent.update(graph=g, static=static, out=out, ws_version=eng.ws.version)
+            except Exception as ex:  # capture is an optimisation of the launch mechanism only: keep the eager launches
+                ent["failed"] = True
+                ent["graph"] = None
+                warnings.warn(f"OmniVGGT: CUDA graph capture failed ({ex!r}); continuing with eager kernel launches")
+                torch.cuda.synchronize()
+                return self._forward_impl(eng, images, extrinsics, intrinsics, depth, mask, depth_idx, cam_idx)
+        for st, t in zip(ent["static"], dyn):
+            if st is not None:
+                st.copy_(t)
+        ent["graph"].replay()
+        out = ent["out"]
+        res = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in out.items() if k not in ("images", "pose_enc_list")}
+        res["pose_enc_list"] = [t.clone() for t in out["pose_enc_list"]]
+        res["pose_enc"] = res["pose_enc_list"][-1]
+        res["images"] = images
+        return res
+
+    def _forward_impl(self, eng, images, extrinsics, intrinsics, depth, mask, depth_idx, cam_idx):
+        B, S, Cin, H, W = images.shape
         ag = self.aggregator
         K = B * S
 
@@ -139,10 +196,13 @@ class OmniVGGT(nn.Module, PyTorchModelHubMixin):
 
         # ---- aux cameras -> pose encoding -> 25 injection vectors (tiny fp32 host math)  (:158-182,:273-287)
         pose = None
+        rows = None
         if len(cam_idx):
-            ci = torch.tensor(cam_idx, device=images.device)
+            ci = eng.cached(("cam_idx", tuple(cam_idx)), lambda: torch.tensor(cam_idx))
+            rows = eng.cached(("cam_rows", B, S, tuple(cam_idx)),
+                              lambda: (torch.arange(B)[:, None] * S + torch.tensor(cam_idx)[None]).reshape(-1))
             pose = TP.aux_pose_encoding(extrinsics.index_select(1, ci), intrinsics.index_select(1, ci), H, W)
-        inj = TP.injection_vectors(eng.inj_pack, pose, cam_idx, B, S)
+        inj = TP.injection_vectors(eng.inj_pack, pose, cam_idx, B, S, rows)
 
         # ---- hot path: aggregator on libovg
         keep = set(self.dpt_layers)

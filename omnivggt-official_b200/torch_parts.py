@@ -151,7 +151,8 @@ def pack_injection(ap):
             torch.stack([m.bias for m in ap.camera_adapters]).float().contiguous())        # [L+1, C]
 
 
-def injection_vectors(pack, pose: Optional[Tensor], cam_idx: List[int], B: int, S: int) -> Tensor:
+def injection_vectors(pack, pose: Optional[Tensor], cam_idx: List[int], B: int, S: int,
+                      rows: Optional[Tensor] = None) -> Tensor:
     """All depth+1 camera injection vectors [L+1, K, C] fp32 in one shot: they depend only on the inputs, not on
     the token stream (reference omnivggt_aggregator.py:172-179,:211,:273-287).  Frames without a camera receive the
     adapter *bias* (the adapter is applied to a zero row).  ``pack`` = pack_injection(aggregator params)."""
@@ -161,7 +162,8 @@ def injection_vectors(pack, pose: Optional[Tensor], cam_idx: List[int], B: int, 
     if pose is not None and len(cam_idx):
         g = torch.einsum("brn,lcn->lbrc", pose.float(), Wp) + bp[:, None, None, :]      # [L+1,B,Sc,C]
         inj = torch.einsum("lbrc,ldc->lbrd", g, Wa) + ba[:, None, None, :]
-        rows = (torch.arange(B)[:, None] * S + torch.tensor(cam_idx)[None]).reshape(-1).to(out.device)
+        if rows is None:     # frame rows b*S + idx (pass a cached device tensor to avoid a host->device copy per call)
+            rows = (torch.arange(B)[:, None] * S + torch.tensor(cam_idx)[None]).reshape(-1).to(out.device)
         out[:, rows] = inj.reshape(L1, -1, C)
     return out.contiguous()
 
