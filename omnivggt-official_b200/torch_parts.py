@@ -118,7 +118,7 @@ def rotmat_to_quat_xyzw(R: Tensor) -> Tensor:
     cand = cand / (2.0 * q_abs[..., None].clamp(min=0.1))
     best = q_abs.argmax(-1)
     rijk = torch.gather(cand, -2, best[..., None, None].expand(best.shape + (1, 4))).squeeze(-2)
-    q = rijk[..., [1, 2, 3, 0]]
+    q = torch.cat([rijk[..., 1:], rijk[..., :1]], -1)     # rijk -> ijkr (no index tensors: CUDA-graph capturable)
     return torch.where(q[..., 3:4] < 0, -q, q)
 
 
