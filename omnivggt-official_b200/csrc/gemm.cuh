@@ -142,17 +142,26 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const uint32_
         if (which < 2 && p.qk_norm) {
           const float* w = which == 0 ? p.qn_w : p.kn_w;
           const float* b = which == 0 ? p.qn_b : p.kn_b;
-          float mean = 0.f;
+          // four independent partial sums: a single serial fp32 chain of 64 adds is ~256 clk of pure latency
+          float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
-          for (int i = 0; i < 64; ++i) mean += v[i];
-          mean *= (1.0f / 64.0f);
-          float var = 0.f;
-#pragma unroll
-          for (int i = 0; i < 64; ++i) {
-            const float d = v[i] - mean;
-            var += d * d;
+          for (int i = 0; i < 64; i += 4) {
+            s0 += v[i];
+            s1 += v[i + 1];
+            s2 += v[i + 2];
+            s3 += v[i + 3];
           }
-          const float rstd = rsqrtf(var * (1.0f / 64.0f) + 1e-5f);
+          const float mean = ((s0 + s1) + (s2 + s3)) * (1.0f / 64.0f);
+          float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+#pragma unroll
+          for (int i = 0; i < 64; i += 4) {
+            const float d0 = v[i] - mean, d1 = v[i + 1] - mean, d2 = v[i + 2] - mean, d3 = v[i + 3] - mean;
+            q0 = fmaf(d0, d0, q0);
+            q1 = fmaf(d1, d1, q1);
+            q2 = fmaf(d2, d2, q2);
+            q3 = fmaf(d3, d3, q3);
+          }
+          const float rstd = rsqrtf(((q0 + q1) + (q2 + q3)) * (1.0f / 64.0f) + 1e-5f);
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const float4 w4 = __ldg(reinterpret_cast<const float4*>(w) + i);
