@@ -39,7 +39,7 @@ struct AttnParams {
 constexpr int ATT_THREADS = 384;
 constexpr int ATT_KV_STAGES = 4;
 constexpr int ATT_TILE_BYTES = 128 * 64 * 2;
-constexpr int ATT_SMEM_BYTES = 1024 + (2 + 2 * ATT_KV_STAGES) * ATT_TILE_BYTES + 512;
+constexpr int ATT_SMEM_BYTES = 1024 + (2 + 2 * ATT_KV_STAGES) * ATT_TILE_BYTES + 512 + 4096;   // barriers + row exchange
 
 template <int N>
 __device__ __forceinline__ void reg_alloc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
@@ -87,7 +87,13 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
-__global__ void __launch_bounds__(ATT_THREADS, 1)
+// HALF = false: 8 softmax warps, one thread per query row (384 threads).
+// HALF = true : 16 softmax warps, two threads per query row (64 key columns each, 640 threads): four softmax warps per SM
+//               sub-partition instead of two, so the fixed per-step latencies of one warp (barrier round trips, TMEM
+//               load/store waits: ~500 of ~2500 clk) are covered by the exp phases of three others.
+constexpr int ATT_THREADS_HALF = 640;
+template <bool HALF>
+__global__ void __launch_bounds__(HALF ? ATT_THREADS_HALF : ATT_THREADS, 1)
 attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
             const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
   constexpr int NS = ATT_KV_STAGES;
@@ -107,6 +113,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
   uint64_t* o_ready = p_full + 2;      // [2]
   uint64_t* s_taken = o_ready + 2;     // [2]  softmax has the S tile in registers -> S buffer may be overwritten
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_taken + 2);
+  float* s_xch = reinterpret_cast<float*>(bars + 64);   // HALF: [2 slots][2 tiles][2 halves][128 rows] row-max / row-sum exchange
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -123,9 +130,9 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
     for (int i = 0; i < 2; ++i) {
       mbar_init(&q_full[i], 1);
       mbar_init(&s_full[i], 1);
-      mbar_init(&p_full[i], 4);
+      mbar_init(&p_full[i], HALF ? 8 : 4);
       mbar_init(&o_ready[i], 1);
-      mbar_init(&s_taken[i], 4);
+      mbar_init(&s_taken[i], HALF ? 8 : 4);
     }
     for (int i = 0; i < NS; ++i) {
       mbar_init(&k_full[i], 1);
@@ -144,8 +151,11 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  // register budget after the split must stay <= 168 * 384 = 64512 (the launch allocation): 128*72 + 256*208 = 62464
-  if (warp < 4) reg_dealloc<72>();
+  // register budget after the split must stay <= the launch allocation: 168 * 384 = 64512 (128*72 + 256*208 = 62464);
+  // HALF: 96 * 640 = 61440 (128*56 + 512*104 = 60416)
+  if (warp < 4) {
+    if constexpr (HALF) reg_dealloc<56>(); else reg_dealloc<72>();
+  }
   if (warp == 0) {
     if (lane == 0) {
       mbar_expect_tx(&q_full[0], ATT_TILE_BYTES);
@@ -224,138 +234,254 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
       }
     }
   } else if (warp >= 4) {
-    reg_alloc<208>();
-    const int t = (warp - 4) >> 2;
-    if (t == 0 || two) {
-      const int quarter = warp & 3;
-      const int r = quarter * 32 + lane;
-      const int qrow = q0 + t * 128 + r;
-      const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
-      const uint32_t tS = tmem_base + t * 128 + lane_off;
-      const uint32_t tP = tmem_base + 256 + t * 64 + lane_off;
-      const uint32_t tO = tmem_base + 384 + t * 64 + lane_off;
-      float m_used = -INFINITY;
-      float l = 0.f;
-#ifdef OVG_ATT_PROFILE
-      const bool prof_on = p.prof && blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0 && (warp & 3) == 0 && lane == 0;
-      long long prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-#endif
-      for (int j = 0; j < nkv; ++j) {
-        const int kv_valid = min(128, p.n - j * 128);
-        ATT_T(t_a);
-        mbar_wait(&s_full[t], j & 1);
-        tc_fence_after();
-        ATT_T(t_b);
-        // ---- whole S row (128 fp32) into registers in one shot
-        uint32_t raw[128];
-        tmem_ld32(tS, raw);
-        tmem_ld32(tS + 32, raw + 32);
-        tmem_ld32(tS + 64, raw + 64);
-        tmem_ld32(tS + 96, raw + 96);
-        tmem_ld_wait();
-        ATT_T(t_c);
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&s_taken[t]);   // S buffer free: the MMA warp may start S(j+1)
-        if (kv_valid != 128) {
-#pragma unroll
-          for (int i = 0; i < 128; ++i)
-            if (i >= kv_valid) raw[i] = 0xff800000u;   // -inf: excluded from the max, exp2 -> 0
-        }
-        float mx0 = -INFINITY, mx1 = -INFINITY;
-#pragma unroll
-        for (int i = 0; i < 128; i += 4) {
-          mx0 = fmaxf(fmaxf(mx0, __uint_as_float(raw[i])), __uint_as_float(raw[i + 1]));
-          mx1 = fmaxf(fmaxf(mx1, __uint_as_float(raw[i + 2])), __uint_as_float(raw[i + 3]));
-        }
-        const float m_new = fmaxf(m_used, fmaxf(mx0, mx1));
-        if (j == 0) {
-          m_used = m_new;
-        } else {
-          // PV(j-1) complete: O is stable (rescale below) and P(j-1) has been read (P buffer reusable)
-          ATT_T(t_d);
-          mbar_wait(&o_ready[t], (j - 1) & 1);
+    if constexpr (HALF) {
+      reg_alloc<104>();
+      const int sw = warp - 4;               // 0..15
+      const int t = sw >> 3;                 // query tile
+      if (t == 0 || two) {
+        const int quarter = warp & 3;        // TMEM lane quarter (hardware: 32 * (warp % 4))
+        const int half = (sw >> 2) & 1;      // key columns [64*half, 64*half + 64) of every S tile
+        const int r = quarter * 32 + lane;
+        const int qrow = q0 + t * 128 + r;
+        const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
+        const uint32_t tS = tmem_base + t * 128 + half * 64 + lane_off;
+        const uint32_t tP = tmem_base + 256 + t * 64 + half * 32 + lane_off;
+        const uint32_t tO = tmem_base + 384 + t * 64 + half * 32 + lane_off;
+        const int bar_id = 1 + t * 4 + quarter;      // named barrier shared by the two warps that own the same rows
+        float m_used = -INFINITY;
+        float l = 0.f;
+        for (int j = 0; j < nkv; ++j) {
+          const int kv_valid = min(128, p.n - j * 128) - half * 64;   // valid columns of this half (may be <= 0)
+          mbar_wait(&s_full[t], j & 1);
           tc_fence_after();
-          ATT_T(t_e);
-          ATT_ACC(2, t_d, t_e);
-          const bool need = (m_new - m_used) > 8.0f;
-          if (__any_sync(0xffffffffu, need)) {
-            const float alpha = need ? ex2_approx(m_used - m_new) : 1.0f;
-            if (need) {
-              m_used = m_new;
-              l *= alpha;
-            }
+          uint32_t raw[64];
+          tmem_ld32(tS, raw);
+          tmem_ld32(tS + 32, raw + 32);
+          tmem_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&s_taken[t]);
+          if (kv_valid < 64) {
 #pragma unroll
-            for (int c = 0; c < 2; ++c) {
+            for (int i = 0; i < 64; ++i)
+              if (i >= kv_valid) raw[i] = 0xff800000u;
+          }
+          float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+          for (int i = 0; i < 64; i += 4) {
+            mx0 = fmaxf(fmaxf(mx0, __uint_as_float(raw[i])), __uint_as_float(raw[i + 1]));
+            mx1 = fmaxf(fmaxf(mx1, __uint_as_float(raw[i + 2])), __uint_as_float(raw[i + 3]));
+          }
+          // row max = max over both halves: exchange through smem (double-buffered by step parity)
+          float* xs = s_xch + (((j & 1) * 2 + t) * 2) * 128;
+          xs[half * 128 + r] = fmaxf(mx0, mx1);
+          asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+          const float m_new = fmaxf(m_used, fmaxf(xs[r], xs[128 + r]));
+          if (j == 0) {
+            m_used = m_new;
+          } else {
+            mbar_wait(&o_ready[t], (j - 1) & 1);     // PV(j-1) done: O stable, P buffer reusable
+            tc_fence_after();
+            const bool need = (m_new - m_used) > 8.0f;       // identical in both halves (same inputs)
+            if (__any_sync(0xffffffffu, need)) {
+              const float alpha = need ? ex2_approx(m_used - m_new) : 1.0f;
+              if (need) {
+                m_used = m_new;
+                l *= alpha;
+              }
               uint32_t o[32];
-              tmem_ld32(tO + c * 32, o);
+              tmem_ld32(tO, o);
               tmem_ld_wait();
 #pragma unroll
               for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-              tmem_st32(tO + c * 32, o);
+              tmem_st32(tO, o);
+              tmem_st_wait();
             }
-            tmem_st_wait();
+          }
+          const float2 negm = make_float2(-m_used, -m_used);
+          float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            uint32_t pk[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              float2 x = make_float2(__uint_as_float(raw[c * 32 + 2 * i]), __uint_as_float(raw[c * 32 + 2 * i + 1]));
+              x = fadd2(x, negm);
+              if (i >= 16 - OVG_ATT_EMU_PAIRS) {
+                x = exp2_poly2(x);
+              } else {
+                x.x = ex2_approx(x.x);
+                x.y = ex2_approx(x.y);
+              }
+              acc = fadd2(acc, x);
+              pk[i] = pack_bf16(x.x, x.y);
+            }
+            tmem_st16(tP + c * 16, pk);
+          }
+          l += acc.x + acc.y;
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&p_full[t]);
+        }
+        // ---- epilogue: l = l_half0 + l_half1; this thread writes 32 of the row's 64 output columns
+        float* xs = s_xch + (((nkv & 1) * 2 + t) * 2) * 128;
+        xs[half * 128 + r] = l;
+        asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+        const float inv = 1.0f / (xs[r] + xs[128 + r]);
+        mbar_wait(&o_ready[t], (nkv - 1) & 1);
+        tc_fence_after();
+        uint32_t o[32];
+        tmem_ld32(tO, o);
+        tmem_ld_wait();
+        if (qrow < p.n) {
+          uint4* dst = reinterpret_cast<uint4*>(p.out + (static_cast<long long>(blockIdx.z) * p.n + qrow) * p.C +
+                                                head * 64 + half * 32);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            uint4 w;
+            w.x = pack_bf16(__uint_as_float(o[8 * i + 0]) * inv, __uint_as_float(o[8 * i + 1]) * inv);
+            w.y = pack_bf16(__uint_as_float(o[8 * i + 2]) * inv, __uint_as_float(o[8 * i + 3]) * inv);
+            w.z = pack_bf16(__uint_as_float(o[8 * i + 4]) * inv, __uint_as_float(o[8 * i + 5]) * inv);
+            w.w = pack_bf16(__uint_as_float(o[8 * i + 6]) * inv, __uint_as_float(o[8 * i + 7]) * inv);
+            dst[i] = w;
           }
         }
-        // ---- P = exp2(S - m) (packed f32x2 subtract / accumulate), bf16 pack into the S columns
-        const float2 negm = make_float2(-m_used, -m_used);
-        float2 acc = make_float2(0.f, 0.f);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          uint32_t pk[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            float2 x = make_float2(__uint_as_float(raw[c * 32 + 2 * i]), __uint_as_float(raw[c * 32 + 2 * i + 1]));
-            x = fadd2(x, negm);
-            if (i >= 16 - OVG_ATT_EMU_PAIRS) {
-              x = exp2_poly2(x);
-            } else {
-              x.x = ex2_approx(x.x);
-              x.y = ex2_approx(x.y);
-            }
-            acc = fadd2(acc, x);
-            pk[i] = pack_bf16(x.x, x.y);
+      }
+    } else {
+    reg_alloc<208>();
+      const int t = (warp - 4) >> 2;
+      if (t == 0 || two) {
+        const int quarter = warp & 3;
+        const int r = quarter * 32 + lane;
+        const int qrow = q0 + t * 128 + r;
+        const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
+        const uint32_t tS = tmem_base + t * 128 + lane_off;
+        const uint32_t tP = tmem_base + 256 + t * 64 + lane_off;
+        const uint32_t tO = tmem_base + 384 + t * 64 + lane_off;
+        float m_used = -INFINITY;
+        float l = 0.f;
+  #ifdef OVG_ATT_PROFILE
+        const bool prof_on = p.prof && blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0 && (warp & 3) == 0 && lane == 0;
+        long long prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  #endif
+        for (int j = 0; j < nkv; ++j) {
+          const int kv_valid = min(128, p.n - j * 128);
+          ATT_T(t_a);
+          mbar_wait(&s_full[t], j & 1);
+          tc_fence_after();
+          ATT_T(t_b);
+          // ---- whole S row (128 fp32) into registers in one shot
+          uint32_t raw[128];
+          tmem_ld32(tS, raw);
+          tmem_ld32(tS + 32, raw + 32);
+          tmem_ld32(tS + 64, raw + 64);
+          tmem_ld32(tS + 96, raw + 96);
+          tmem_ld_wait();
+          ATT_T(t_c);
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&s_taken[t]);   // S buffer free: the MMA warp may start S(j+1)
+          if (kv_valid != 128) {
+  #pragma unroll
+            for (int i = 0; i < 128; ++i)
+              if (i >= kv_valid) raw[i] = 0xff800000u;   // -inf: excluded from the max, exp2 -> 0
           }
-          tmem_st16(tP + c * 16, pk);
+          float mx0 = -INFINITY, mx1 = -INFINITY;
+  #pragma unroll
+          for (int i = 0; i < 128; i += 4) {
+            mx0 = fmaxf(fmaxf(mx0, __uint_as_float(raw[i])), __uint_as_float(raw[i + 1]));
+            mx1 = fmaxf(fmaxf(mx1, __uint_as_float(raw[i + 2])), __uint_as_float(raw[i + 3]));
+          }
+          const float m_new = fmaxf(m_used, fmaxf(mx0, mx1));
+          if (j == 0) {
+            m_used = m_new;
+          } else {
+            // PV(j-1) complete: O is stable (rescale below) and P(j-1) has been read (P buffer reusable)
+            ATT_T(t_d);
+            mbar_wait(&o_ready[t], (j - 1) & 1);
+            tc_fence_after();
+            ATT_T(t_e);
+            ATT_ACC(2, t_d, t_e);
+            const bool need = (m_new - m_used) > 8.0f;
+            if (__any_sync(0xffffffffu, need)) {
+              const float alpha = need ? ex2_approx(m_used - m_new) : 1.0f;
+              if (need) {
+                m_used = m_new;
+                l *= alpha;
+              }
+  #pragma unroll
+              for (int c = 0; c < 2; ++c) {
+                uint32_t o[32];
+                tmem_ld32(tO + c * 32, o);
+                tmem_ld_wait();
+  #pragma unroll
+                for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                tmem_st32(tO + c * 32, o);
+              }
+              tmem_st_wait();
+            }
+          }
+          // ---- P = exp2(S - m) (packed f32x2 subtract / accumulate), bf16 pack into the S columns
+          const float2 negm = make_float2(-m_used, -m_used);
+          float2 acc = make_float2(0.f, 0.f);
+  #pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint32_t pk[16];
+  #pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              float2 x = make_float2(__uint_as_float(raw[c * 32 + 2 * i]), __uint_as_float(raw[c * 32 + 2 * i + 1]));
+              x = fadd2(x, negm);
+              if (i >= 16 - OVG_ATT_EMU_PAIRS) {
+                x = exp2_poly2(x);
+              } else {
+                x.x = ex2_approx(x.x);
+                x.y = ex2_approx(x.y);
+              }
+              acc = fadd2(acc, x);
+              pk[i] = pack_bf16(x.x, x.y);
+            }
+            tmem_st16(tP + c * 16, pk);
+          }
+          l += acc.x + acc.y;
+          ATT_T(t_f);
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&p_full[t]);
+          ATT_T(t_g);
+          ATT_ACC(0, t_a, t_b);   // wait for S
+          ATT_ACC(1, t_b, t_c);   // TMEM read of the S row
+          ATT_ACC(3, t_c, t_f);   // max + (o_ready wait) + exp + P store issue
+          ATT_ACC(4, t_f, t_g);   // wait::st + fence + arrive
+          ATT_ACC(5, t_a, t_g);   // whole step
         }
-        l += acc.x + acc.y;
-        ATT_T(t_f);
-        tmem_st_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&p_full[t]);
-        ATT_T(t_g);
-        ATT_ACC(0, t_a, t_b);   // wait for S
-        ATT_ACC(1, t_b, t_c);   // TMEM read of the S row
-        ATT_ACC(3, t_c, t_f);   // max + (o_ready wait) + exp + P store issue
-        ATT_ACC(4, t_f, t_g);   // wait::st + fence + arrive
-        ATT_ACC(5, t_a, t_g);   // whole step
-      }
-#ifdef OVG_ATT_PROFILE
-      if (prof_on) {
-        for (int i = 0; i < 8; ++i) p.prof[t * 8 + i] = prof_acc[i];
-        p.prof[t * 8 + 7] = nkv;
-      }
-#endif
-      // ---- epilogue: O / l -> bf16 -> out[b, qrow, head*64 .. +64)
-      mbar_wait(&o_ready[t], (nkv - 1) & 1);
-      tc_fence_after();
-      const float inv = 1.0f / l;
-      uint32_t o[64];
-      tmem_ld32(tO, o);
-      tmem_ld32(tO + 32, o + 32);
-      tmem_ld_wait();
-      if (qrow < p.n) {
-        uint4* dst = reinterpret_cast<uint4*>(p.out + (static_cast<long long>(blockIdx.z) * p.n + qrow) * p.C +
-                                              head * 64);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          uint4 w;
-          w.x = pack_bf16(__uint_as_float(o[8 * i + 0]) * inv, __uint_as_float(o[8 * i + 1]) * inv);
-          w.y = pack_bf16(__uint_as_float(o[8 * i + 2]) * inv, __uint_as_float(o[8 * i + 3]) * inv);
-          w.z = pack_bf16(__uint_as_float(o[8 * i + 4]) * inv, __uint_as_float(o[8 * i + 5]) * inv);
-          w.w = pack_bf16(__uint_as_float(o[8 * i + 6]) * inv, __uint_as_float(o[8 * i + 7]) * inv);
-          dst[i] = w;
+  #ifdef OVG_ATT_PROFILE
+        if (prof_on) {
+          for (int i = 0; i < 8; ++i) p.prof[t * 8 + i] = prof_acc[i];
+          p.prof[t * 8 + 7] = nkv;
+        }
+  #endif
+        // ---- epilogue: O / l -> bf16 -> out[b, qrow, head*64 .. +64)
+        mbar_wait(&o_ready[t], (nkv - 1) & 1);
+        tc_fence_after();
+        const float inv = 1.0f / l;
+        uint32_t o[64];
+        tmem_ld32(tO, o);
+        tmem_ld32(tO + 32, o + 32);
+        tmem_ld_wait();
+        if (qrow < p.n) {
+          uint4* dst = reinterpret_cast<uint4*>(p.out + (static_cast<long long>(blockIdx.z) * p.n + qrow) * p.C +
+                                                head * 64);
+  #pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            uint4 w;
+            w.x = pack_bf16(__uint_as_float(o[8 * i + 0]) * inv, __uint_as_float(o[8 * i + 1]) * inv);
+            w.y = pack_bf16(__uint_as_float(o[8 * i + 2]) * inv, __uint_as_float(o[8 * i + 3]) * inv);
+            w.z = pack_bf16(__uint_as_float(o[8 * i + 4]) * inv, __uint_as_float(o[8 * i + 5]) * inv);
+            w.w = pack_bf16(__uint_as_float(o[8 * i + 6]) * inv, __uint_as_float(o[8 * i + 7]) * inv);
+            dst[i] = w;
+          }
         }
       }
     }

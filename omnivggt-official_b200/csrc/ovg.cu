@@ -16,6 +16,7 @@ namespace {
 
 thread_local std::string g_err;
 std::atomic<long long> g_launches{0};
+const bool g_attn_half = [] { const char* e = getenv("OVG_ATTN_HALF"); return e && e[0] == '1'; }();   // A/B switch
 const bool g_stage_default = [] { const char* e = getenv("OVG_GEMM_STAGE"); return !(e && e[0] == '0'); }();   // A/B switch
 const bool g_pair_default = [] { const char* e = getenv("OVG_GEMM_PAIR"); return !(e && e[0] == '0'); }();   // A/B switch
 
@@ -373,12 +374,16 @@ int ovg_attention(const void* q, const void* k, const void* v, void* out, int ba
   if (rc) return rc;
   static bool attr_set = false;
   if (!attr_set) {
-    OVG_CUDA(cudaFuncSetAttribute(ovg::attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ovg::ATT_SMEM_BYTES));
+    OVG_CUDA(cudaFuncSetAttribute(ovg::attn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ovg::ATT_SMEM_BYTES));
+    OVG_CUDA(cudaFuncSetAttribute(ovg::attn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ovg::ATT_SMEM_BYTES));
     attr_set = true;
   }
   ovg::AttnParams p{n, heads, heads * 64, reinterpret_cast<__nv_bfloat16*>(out), g_attn_prof};
   dim3 grid((n + 255) / 256, heads, batch);
-  ovg::attn_kernel<<<grid, ovg::ATT_THREADS, ovg::ATT_SMEM_BYTES, st>>>(tq, tk, tv, p);
+  if (g_attn_half)
+    ovg::attn_kernel<true><<<grid, ovg::ATT_THREADS_HALF, ovg::ATT_SMEM_BYTES, st>>>(tq, tk, tv, p);
+  else
+    ovg::attn_kernel<false><<<grid, ovg::ATT_THREADS, ovg::ATT_SMEM_BYTES, st>>>(tq, tk, tv, p);
   return post_launch("ovg_attention");
 }
 
