@@ -78,6 +78,9 @@ __device__ __forceinline__ float2 exp2_poly2(float2 x) {
   o.y = __int_as_float(__float_as_int(t.y) * 8388608 + __float_as_int(p.y));
   return o;
 }
+#ifndef OVG_ATT_TOKEN
+#define OVG_ATT_TOKEN 1     // alternate the exp phases of the two query tiles (see the softmax loop)
+#endif
 #ifndef OVG_ATT_EMU_PAIRS
 #define OVG_ATT_EMU_PAIRS 4   // of every 16 element pairs, how many take the polynomial path (0 = all MUFU); 4 measured best
 #endif
@@ -113,6 +116,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
   uint64_t* o_ready = p_full + 2;      // [2]
   uint64_t* s_taken = o_ready + 2;     // [2]  softmax has the S tile in registers -> S buffer may be overwritten
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_taken + 2);
+  uint64_t* mufu_tok = s_taken + 2 + 1;   // [2 tiles][4 SM sub-partitions] (slot after tmem_slot's 8 bytes)
   float* s_xch = reinterpret_cast<float*>(bars + 64);   // HALF: [2 slots][2 tiles][2 halves][128 rows] row-max / row-sum exchange
 
   const int warp = threadIdx.x >> 5;
@@ -134,6 +138,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
       mbar_init(&o_ready[i], 1);
       mbar_init(&s_taken[i], HALF ? 8 : 4);
     }
+    for (int i = 0; i < 8; ++i) mbar_init(&mufu_tok[i], 1);
     for (int i = 0; i < NS; ++i) {
       mbar_init(&k_full[i], 1);
       mbar_init(&k_empty[i], two ? 2 : 1);   // one commit per MMA issuer (tile)
@@ -422,6 +427,13 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
               tmem_st_wait();
             }
           }
+          // ---- MUFU turn-taking.  Warp (4 + q) of tile 0 and warp (8 + q) of tile 1 share SM sub-partition q and its
+          // MUFU (16 ex2/clk/SM is THE bound of this kernel at head_dim 64).  Left alone the two run their exp phases
+          // concurrently at half rate each and idle together during their ~600 clk of barrier / TMEM round trips; a token
+          // per sub-partition makes the exp phases alternate, so one warp's round trips hide under the other's exps.
+          if (OVG_ATT_TOKEN && two) {
+            if (t == 1 || j > 0) mbar_wait(&mufu_tok[t * 4 + quarter], (t == 1 ? j : j - 1) & 1);
+          }
           // ---- P = exp2(S - m) (packed f32x2 subtract / accumulate), bf16 pack into the S columns
           const float2 negm = make_float2(-m_used, -m_used);
           float2 acc = make_float2(0.f, 0.f);
@@ -444,6 +456,10 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
             tmem_st16(tP + c * 16, pk);
           }
           l += acc.x + acc.y;
+          if (OVG_ATT_TOKEN && two) {       // pass the MUFU to the other tile's warp on this sub-partition
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&mufu_tok[(1 - t) * 4 + quarter]);
+          }
           ATT_T(t_f);
           tmem_st_wait();
           tc_fence_before();

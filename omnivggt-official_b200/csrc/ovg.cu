@@ -395,10 +395,12 @@ int ovg_layernorm(const void* in, int in_is_bf16, long long ld_in, void* out, in
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   ovg::LnParams p{in, in_is_bf16, ld_in, out, out_is_f32, ld_out, rows, C, w, b, eps,
                   grp_out, grp_in, grp_off};
-  const int blocks = (rows + 7) / 8;
+  static const int ln_threads = [] { const char* e = getenv("OVG_LN_THREADS"); return e ? atoi(e) : 256; }();   // A/B switch
+  const int rpb = ln_threads / 32;
+  const int blocks = (rows + rpb - 1) / rpb;
   switch (C / 32) {
 #define OVG_LN_CASE(V) \
-  case V: ovg::layernorm_kernel<V><<<blocks, 256, 0, st>>>(p); break;
+  case V: ovg::layernorm_kernel<V><<<blocks, ln_threads, 0, st>>>(p); break;
     OVG_LN_CASE(4) OVG_LN_CASE(8) OVG_LN_CASE(12) OVG_LN_CASE(16) OVG_LN_CASE(20) OVG_LN_CASE(24) OVG_LN_CASE(28)
     OVG_LN_CASE(32) OVG_LN_CASE(36) OVG_LN_CASE(40) OVG_LN_CASE(44) OVG_LN_CASE(48) OVG_LN_CASE(52) OVG_LN_CASE(56)
     OVG_LN_CASE(60) OVG_LN_CASE(64)

@@ -288,9 +288,17 @@ class Engine:
                  skip1=skip1, skip2=skip2, rowmap=L.ROWS_PAD, gh=h, gw=wd)
 
     def dpt_chunk(self, pk: DPTPack, slots: List[torch.Tensor], f0: int, Fc: int, H: int, W: int, head_act: int,
-                  preds: torch.Tensor, conf: torch.Tensor):
-        """One frame chunk of one head (reference heads/dpt_head.py:185-304).  slots: 4 x bf16 [K,T,2C]."""
-        ws, R = self.ws, self.R
+                  preds: torch.Tensor, conf: torch.Tensor, ns: str = ""):
+        """One frame chunk of one head (reference heads/dpt_head.py:185-304).  slots: 4 x bf16 [K,T,2C].
+        ``ns`` namespaces the workspace buffers so that the two heads can run concurrently on different streams."""
+        R = self.R
+        _ws = self.ws
+
+        class _NS:        # thin view of the workspace with prefixed buffer names
+            @staticmethod
+            def get(name, shape, dtype=BF16, zero=False):
+                return _ws.get(ns + name, shape, dtype, zero)
+        ws = _NS
         hp, wp = H // self.patch, W // self.patch
         P, T, C2 = hp * wp, hp * wp + R + 1, 2 * self.C
         aspect = W / H
@@ -364,12 +372,16 @@ class Engine:
                  outc=pk.outc, head_act=head_act, preds=preds[f0:f0 + Fc], conf=conf[f0:f0 + Fc], rowmap=L.ROWS_PAD,
                  gh=Hh, gw=Ww)
 
-    def dpt(self, name: str, slots: Dict[int, torch.Tensor], layers: Sequence[int], K: int, H: int, W: int,
-            head_act: int, chunk: int = 8):
+    def dpt_alloc(self, name: str, K: int, H: int, W: int):
         pk = self.dpt_packs[name]
-        preds = torch.empty(K, H, W, pk.outc - 1, device=self.device, dtype=F32)
-        conf = torch.empty(K, H, W, device=self.device, dtype=F32)
+        return (torch.empty(K, H, W, pk.outc - 1, device=self.device, dtype=F32),
+                torch.empty(K, H, W, device=self.device, dtype=F32))
+
+    def dpt(self, name: str, slots: Dict[int, torch.Tensor], layers: Sequence[int], K: int, H: int, W: int,
+            head_act: int, chunk: int = 8, out=None):
+        pk = self.dpt_packs[name]
+        preds, conf = out if out is not None else self.dpt_alloc(name, K, H, W)
         sl = [slots[i] for i in layers]
         for f0 in range(0, K, chunk):
-            self.dpt_chunk(pk, sl, f0, min(chunk, K - f0), H, W, head_act, preds, conf)
+            self.dpt_chunk(pk, sl, f0, min(chunk, K - f0), H, W, head_act, preds, conf, ns=name + ".")
         return preds, conf

@@ -48,6 +48,8 @@ class OmniVGGT(nn.Module, PyTorchModelHubMixin):
         # replay the ~1000 kernel launches of a forward from a CUDA graph once a shape has been seen twice
         self.use_cuda_graph = (os.environ.get("OVG_CUDA_GRAPH", "1") != "0") if use_cuda_graph is None else use_cuda_graph
         self._graphs = {}
+        self.head_streams = os.environ.get("OVG_HEAD_STREAMS", "1") != "0"   # camera / depth / point heads on 3 streams
+        self._streams = None
         pe = "conv" if "conv" in patch_embed else "dino"
         self.aggregator = AggregatorParams(img_size, patch_size, embed_dim, depth, 64, num_register_tokens, pe,
                                            dino_depth, dino_heads)
@@ -208,15 +210,37 @@ class OmniVGGT(nn.Module, PyTorchModelHubMixin):
         keep = set(self.dpt_layers)
         slots, cam_tokens = eng.aggregate(patch, inj, depth, mask, depth_idx, B, S, H, W, keep)
 
+        # ---- heads.  The camera head and the two DPT heads only read the aggregator outputs: they run on three streams
+        # (forked / joined with events, also inside a captured CUDA graph) so that their many small kernels -- 19^2 / 37^2
+        # feature maps, M = 8 GEMVs -- share the 148 SMs instead of running one after the other.
         predictions: Dict[str, object] = {}
-        pose_list = TP.camera_head(self.camera_head, cam_tokens.view(B, S, -1), dtype=self.camera_dtype)
+        d_out = eng.dpt_alloc("depth_head", K, H, W)
+        p_out = eng.dpt_alloc("point_head", K, H, W)
+        main = torch.cuda.current_stream() if images.is_cuda else None
+        if main is not None and self.head_streams:
+            if self._streams is None:
+                self._streams = (torch.cuda.Stream(), torch.cuda.Stream())
+            s_cam, s_pt = self._streams
+            fork = torch.cuda.Event()
+            fork.record(main)
+            s_cam.wait_event(fork)
+            s_pt.wait_event(fork)
+            with torch.cuda.stream(s_cam):
+                pose_list = TP.camera_head(self.camera_head, cam_tokens.view(B, S, -1), dtype=self.camera_dtype)
+            with torch.cuda.stream(s_pt):
+                eng.dpt("point_head", slots, self.dpt_layers, K, H, W, head_act=1, out=p_out)
+            eng.dpt("depth_head", slots, self.dpt_layers, K, H, W, head_act=0, out=d_out)
+            main.wait_stream(s_cam)
+            main.wait_stream(s_pt)
+        else:
+            pose_list = TP.camera_head(self.camera_head, cam_tokens.view(B, S, -1), dtype=self.camera_dtype)
+            eng.dpt("depth_head", slots, self.dpt_layers, K, H, W, head_act=0, out=d_out)
+            eng.dpt("point_head", slots, self.dpt_layers, K, H, W, head_act=1, out=p_out)
         predictions["pose_enc"] = pose_list[-1]
         predictions["pose_enc_list"] = pose_list
-        d, dc = eng.dpt("depth_head", slots, self.dpt_layers, K, H, W, head_act=0)
-        predictions["depth"] = d.view(B, S, H, W, 1)
-        predictions["depth_conf"] = dc.view(B, S, H, W)
-        p, pc = eng.dpt("point_head", slots, self.dpt_layers, K, H, W, head_act=1)
-        predictions["world_points"] = p.view(B, S, H, W, 3)
-        predictions["world_points_conf"] = pc.view(B, S, H, W)
+        predictions["depth"] = d_out[0].view(B, S, H, W, 1)
+        predictions["depth_conf"] = d_out[1].view(B, S, H, W)
+        predictions["world_points"] = p_out[0].view(B, S, H, W, 3)
+        predictions["world_points_conf"] = p_out[1].view(B, S, H, W)
         predictions["images"] = images
         return predictions
