@@ -35,7 +35,7 @@ KB = os.environ.get("KB", "all")
 S, T, C = int(os.environ.get("S", 8)), 1374, 1024
 M = S * T
 a = torch.randn(M, C, device=dev).to(BF16)
-for name, N, K, bns in () if KB == "attn" else (("qkv", 3072, 1024, (256, 512)), ("proj", 1024, 1024, (128, 256, 512)), ("fc1", 4096, 1024, (256, 512)), ("fc2", 1024, 4096, (128, 256, 512))):
+for name, N, K, bns in () if KB == "attn" else (("qkv", 3072, 1024, (256, 512)), ("proj", 1024, 1024, (384, 512)), ("fc1", 4096, 1024, (256, 512)), ("fc2", 1024, 4096, (384, 512))):
     x = torch.randn(M, K, device=dev).to(BF16)
     w = (torch.randn(N, K, device=dev) * K ** -0.5).to(BF16)
     bias = torch.randn(N, device=dev)
