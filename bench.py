@@ -85,6 +85,12 @@ def run_reference(args, rank, world):
         return
     import torch
     from oracle import cpu_baseline as cb
+    # torchrun exports OMP_NUM_THREADS=1 for multi-rank launches; this arm must use every host core it can get
+    try:
+        ncpu = len(os.sched_getaffinity(0))
+    except AttributeError:
+        ncpu = os.cpu_count() or 1
+    torch.set_num_threads(max(1, ncpu))
     for _ in range(max(args.warmup, 0) and 1):          # one warm-up sample is enough to page in MKL / weights
         cb.sample()
     secs = []
