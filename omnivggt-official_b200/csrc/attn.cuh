@@ -45,20 +45,6 @@ template <int N>
 __device__ __forceinline__ void reg_alloc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N>
 __device__ __forceinline__ void reg_dealloc() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
-__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {   // packed fp32x2 add (sm_100 FADD2)
-  float2 d;
-  asm("add.rn.f32x2 %0, %1, %2;"
-      : "=l"(reinterpret_cast<uint64_t&>(d))
-      : "l"(reinterpret_cast<uint64_t&>(a)), "l"(reinterpret_cast<uint64_t&>(b)));
-  return d;
-}
-__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {   // packed fp32x2 fma (sm_100 FFMA2)
-  float2 d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;"
-      : "=l"(reinterpret_cast<uint64_t&>(d))
-      : "l"(reinterpret_cast<uint64_t&>(a)), "l"(reinterpret_cast<uint64_t&>(b)), "l"(reinterpret_cast<uint64_t&>(c)));
-  return d;
-}
 // exp2 on the FMA pipes for a pair of values (x <= ~8): Cody-Waite split x = n + r, r in [-0.5, 0.5], 2^r by a
 // degree-3 minimax polynomial (max rel. error 1.0e-4, far below bf16 resolution of P), exponent inserted with one IMAD.
 // At head_dim 64 the softmax needs 16 384 exp2 per 128x128 tile against 512 tensor-pipe clocks; the MUFU unit alone
@@ -392,29 +378,66 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
             for (int i = 0; i < 128; ++i)
               if (i >= kv_valid) raw[i] = 0xff800000u;   // -inf: excluded from the max, exp2 -> 0
           }
-          float mx0 = -INFINITY, mx1 = -INFINITY;
+          // ---- Softmax step with a STALE reference.  P(j) = exp2(S - m_used) is computed with the reference left by the
+          // earlier steps while the row maximum of THIS step is gathered in the same pass (FMNMX3 on the ALU pipe next to
+          // the MUFU / FMA work) instead of in a separate max phase in front of it; the two softmax warps of an SM
+          // sub-partition run in lock-step, so a separate max phase left the MUFU idle in both.  Exactness: the reference
+          // only has to be within 2^8 of the running maximum (it cancels in O / l).  If this step's maximum exceeds it
+          // by more than that (always at j = 0, rare afterwards) the step is redone from the S row still held in
+          // registers: O and l are rescaled and P recomputed against the new maximum -- same arithmetic as before.
+          float2 acc = make_float2(0.f, 0.f);
+          bool slow = (j == 0);
+          float m_new = m_used;
+          if (j > 0) {
+            const float2 negm = make_float2(-m_used, -m_used);
+            float mx0 = -INFINITY, mx1 = -INFINITY;
   #pragma unroll
-          for (int i = 0; i < 128; i += 4) {
-            mx0 = fmaxf(fmaxf(mx0, __uint_as_float(raw[i])), __uint_as_float(raw[i + 1]));
-            mx1 = fmaxf(fmaxf(mx1, __uint_as_float(raw[i + 2])), __uint_as_float(raw[i + 3]));
+            for (int c = 0; c < 4; ++c) {
+              uint32_t pk[16];
+  #pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const float r0 = __uint_as_float(raw[c * 32 + 2 * i]), r1 = __uint_as_float(raw[c * 32 + 2 * i + 1]);
+                if (i & 1) mx1 = fmaxf(fmaxf(mx1, r0), r1); else mx0 = fmaxf(fmaxf(mx0, r0), r1);
+                float2 x = fadd2(make_float2(r0, r1), negm);
+                if (i >= 16 - OVG_ATT_EMU_PAIRS) {
+                  x = exp2_poly2(x);
+                } else {
+                  x.x = ex2_approx(x.x);
+                  x.y = ex2_approx(x.y);
+                }
+                acc = fadd2(acc, x);
+                pk[i] = pack_bf16(x.x, x.y);
+              }
+              if (c == 0) {
+                // PV(j-1) complete: P(j-1) has been read (P buffer reusable) and O is stable (rescale below)
+                ATT_T(t_d);
+                mbar_wait(&o_ready[t], (j - 1) & 1);
+                tc_fence_after();
+                ATT_T(t_e);
+                ATT_ACC(2, t_d, t_e);
+              }
+              tmem_st16(tP + c * 16, pk);
+            }
+            m_new = fmaxf(m_used, fmaxf(mx0, mx1));
+            slow = __any_sync(0xffffffffu, (m_new - m_used) > 8.0f);
           }
-          const float m_new = fmaxf(m_used, fmaxf(mx0, mx1));
-          if (j == 0) {
-            m_used = m_new;
-          } else {
-            // PV(j-1) complete: O is stable (rescale below) and P(j-1) has been read (P buffer reusable)
-            ATT_T(t_d);
-            mbar_wait(&o_ready[t], (j - 1) & 1);
-            tc_fence_after();
-            ATT_T(t_e);
-            ATT_ACC(2, t_d, t_e);
-            const bool need = (m_new - m_used) > 8.0f;
-            if (__any_sync(0xffffffffu, need)) {
+          if (slow) {
+            if (j == 0) {
+              float mx0 = -INFINITY, mx1 = -INFINITY;
+  #pragma unroll
+              for (int i = 0; i < 128; i += 4) {
+                mx0 = fmaxf(fmaxf(mx0, __uint_as_float(raw[i])), __uint_as_float(raw[i + 1]));
+                mx1 = fmaxf(fmaxf(mx1, __uint_as_float(raw[i + 2])), __uint_as_float(raw[i + 3]));
+              }
+              m_used = fmaxf(mx0, mx1);
+            } else {
+              const bool need = (m_new - m_used) > 8.0f;
               const float alpha = need ? ex2_approx(m_used - m_new) : 1.0f;
               if (need) {
                 m_used = m_new;
                 l *= alpha;
               }
+              tmem_st_wait();               // the P stores of the fast pass are re-issued below
   #pragma unroll
               for (int c = 0; c < 2; ++c) {
                 uint32_t o[32];
@@ -424,42 +447,25 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
                 for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
                 tmem_st32(tO + c * 32, o);
               }
-              tmem_st_wait();
             }
-          }
-          // ---- MUFU turn-taking.  Warp (4 + q) of tile 0 and warp (8 + q) of tile 1 share SM sub-partition q and its
-          // MUFU (16 ex2/clk/SM is THE bound of this kernel at head_dim 64).  Left alone the two run their exp phases
-          // concurrently at half rate each and idle together during their ~600 clk of barrier / TMEM round trips; a token
-          // per sub-partition makes the exp phases alternate, so one warp's round trips hide under the other's exps.
-          if (OVG_ATT_TOKEN && two) {
-            if (t == 1 || j > 0) mbar_wait(&mufu_tok[t * 4 + quarter], (t == 1 ? j : j - 1) & 1);
-          }
-          // ---- P = exp2(S - m) (packed f32x2 subtract / accumulate), bf16 pack into the S columns
-          const float2 negm = make_float2(-m_used, -m_used);
-          float2 acc = make_float2(0.f, 0.f);
+            const float2 negm = make_float2(-m_used, -m_used);
+            acc = make_float2(0.f, 0.f);
   #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            uint32_t pk[16];
+            for (int c = 0; c < 4; ++c) {
+              uint32_t pk[16];
   #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              float2 x = make_float2(__uint_as_float(raw[c * 32 + 2 * i]), __uint_as_float(raw[c * 32 + 2 * i + 1]));
-              x = fadd2(x, negm);
-              if (i >= 16 - OVG_ATT_EMU_PAIRS) {
-                x = exp2_poly2(x);
-              } else {
+              for (int i = 0; i < 16; ++i) {
+                float2 x = make_float2(__uint_as_float(raw[c * 32 + 2 * i]), __uint_as_float(raw[c * 32 + 2 * i + 1]));
+                x = fadd2(x, negm);
                 x.x = ex2_approx(x.x);
                 x.y = ex2_approx(x.y);
+                acc = fadd2(acc, x);
+                pk[i] = pack_bf16(x.x, x.y);
               }
-              acc = fadd2(acc, x);
-              pk[i] = pack_bf16(x.x, x.y);
+              tmem_st16(tP + c * 16, pk);
             }
-            tmem_st16(tP + c * 16, pk);
           }
           l += acc.x + acc.y;
-          if (OVG_ATT_TOKEN && two) {       // pass the MUFU to the other tile's warp on this sub-partition
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&mufu_tok[(1 - t) * 4 + quarter]);
-          }
           ATT_T(t_f);
           tmem_st_wait();
           tc_fence_before();

@@ -31,14 +31,10 @@ struct LnParams {
   int grp_out, grp_in, grp_off;
 };
 
-template <int VPL>  // values per lane = C / 32 (multiple of 4)
-__global__ void __launch_bounds__(256) layernorm_kernel(const LnParams p) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (warp >= p.rows) return;
-  long long src = warp;
-  if (p.grp_out > 0) src = static_cast<long long>(warp / p.grp_out) * p.grp_in + p.grp_off + (warp % p.grp_out);
-  float v[VPL];
+template <int VPL>
+__device__ __forceinline__ void ln_load_row(const LnParams& p, const int row, const int lane, float (&v)[VPL]) {
+  long long src = row;
+  if (p.grp_out > 0) src = static_cast<long long>(row / p.grp_out) * p.grp_in + p.grp_off + (row % p.grp_out);
   // lane handles chunks of 4 consecutive elements: element index = (i*32 + lane)*4 + e
   if (p.in_bf16) {
     const __nv_bfloat16* x = reinterpret_cast<const __nv_bfloat16*>(p.in) + src * p.ld_in;
@@ -61,34 +57,66 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const LnParams p) {
       v[4 * i + 3] = f.w;
     }
   }
-  float s = 0.f;
-#pragma unroll
-  for (int i = 0; i < VPL; ++i) s += v[i];
-  const float mean = warp_sum(s) / p.C;
-  float q = 0.f;
-#pragma unroll
-  for (int i = 0; i < VPL; ++i) {
-    const float d = v[i] - mean;
-    q += d * d;
-  }
-  const float rstd = rsqrtf(warp_sum(q) / p.C + p.eps);
-#pragma unroll
-  for (int i = 0; i < VPL / 4; ++i) {
-    const int c = (i * 32 + lane) * 4;
-    float o[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      o[e] = (v[4 * i + e] - mean) * rstd;
-      if (p.w) o[e] = o[e] * __ldg(p.w + c + e) + __ldg(p.b + c + e);
-    }
-    if (p.out_f32) {
-      *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + static_cast<long long>(warp) * p.ld_out + c) =
-          make_float4(o[0], o[1], o[2], o[3]);
+}
+
+// Persistent: the grid is sized to the machine (ovg.cu) and every warp walks rows with a grid stride, loading row i+1
+// while it reduces row i, so the HBM stream never drains between "waves" of short-lived blocks.
+template <int VPL>  // values per lane = C / 32 (multiple of 4)
+__global__ void __launch_bounds__(256, 2) layernorm_kernel(const LnParams p) {
+  constexpr bool PF = VPL <= 32;     // two rows of C = 2048 do not fit the register budget of 2 blocks / SM
+  const int lane = threadIdx.x & 31;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (row >= p.rows) return;
+  float v[VPL], nx[PF ? VPL : 4];
+  if (PF) ln_load_row<VPL>(p, row, lane, v);
+  for (; row < p.rows; row += nwarps) {
+    const bool more = PF && row + nwarps < p.rows;
+    if constexpr (PF) {
+      if (more) ln_load_row<VPL>(p, row + nwarps, lane, reinterpret_cast<float (&)[VPL]>(nx));
     } else {
-      uint2 u;
-      u.x = pack_bf16(o[0], o[1]);
-      u.y = pack_bf16(o[2], o[3]);
-      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<long long>(warp) * p.ld_out + c) = u;
+      ln_load_row<VPL>(p, row, lane, v);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) s += v[i];
+    const float mean = warp_sum(s) / p.C;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const float d = v[i] - mean;
+      q += d * d;
+    }
+    const float rstd = rsqrtf(warp_sum(q) / p.C + p.eps);
+#pragma unroll
+    for (int i = 0; i < VPL / 4; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      float o[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) o[e] = (v[4 * i + e] - mean) * rstd;
+      if (p.w) {
+        const float4 w4 = __ldg(reinterpret_cast<const float4*>(p.w + c));
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.b + c));
+        o[0] = fmaf(o[0], w4.x, b4.x);
+        o[1] = fmaf(o[1], w4.y, b4.y);
+        o[2] = fmaf(o[2], w4.z, b4.z);
+        o[3] = fmaf(o[3], w4.w, b4.w);
+      }
+      if (p.out_f32) {
+        *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + static_cast<long long>(row) * p.ld_out + c) =
+            make_float4(o[0], o[1], o[2], o[3]);
+      } else {
+        uint2 u;
+        u.x = pack_bf16(o[0], o[1]);
+        u.y = pack_bf16(o[2], o[3]);
+        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<long long>(row) * p.ld_out + c) = u;
+      }
+    }
+    if constexpr (PF) {
+      if (more) {
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) v[i] = nx[i];
+      }
     }
   }
 }

@@ -305,6 +305,9 @@ int ovg_gemm(const ovg_gemm_args* a, void* stream) {
     OVG_REQUIRE(a->out && a->gamma && a->bias, "RESID needs out, gamma, bias");
   } else if (a->epi == OVG_EPI_BF16) {
     OVG_REQUIRE(a->out, "BF16 epilogue needs out");
+    OVG_REQUIRE((reinterpret_cast<uintptr_t>(a->bias) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->table) & 15) == 0 &&
+                    (a->table == nullptr || a->n % 4 == 0),
+                "bias / table must be 16-byte aligned");
     if (a->rowmap == OVG_ROWS_PIXSHUF)
       OVG_REQUIRE(a->ps > 0 && a->cout % 32 == 0 && a->n == a->ps * a->ps * a->cout, "PIXSHUF geometry");
     if (a->rowmap != OVG_ROWS_IDENT) OVG_REQUIRE(a->gh > 0 && a->gw > 0, "row map needs gh, gw");
@@ -396,8 +399,11 @@ int ovg_layernorm(const void* in, int in_is_bf16, long long ld_in, void* out, in
   ovg::LnParams p{in, in_is_bf16, ld_in, out, out_is_f32, ld_out, rows, C, w, b, eps,
                   grp_out, grp_in, grp_off};
   static const int ln_threads = [] { const char* e = getenv("OVG_LN_THREADS"); return e ? atoi(e) : 256; }();   // A/B switch
+  static const int ln_persist = [] { const char* e = getenv("OVG_LN_PERSIST"); return e ? atoi(e) : 2; }();     // blocks per SM (0: one row per warp)
+  OVG_REQUIRE((reinterpret_cast<uintptr_t>(w) & 15) == 0 && (reinterpret_cast<uintptr_t>(b) & 15) == 0, "w / b must be 16-byte aligned");
   const int rpb = ln_threads / 32;
-  const int blocks = (rows + rpb - 1) / rpb;
+  int blocks = (rows + rpb - 1) / rpb;
+  if (ln_persist > 0 && blocks > 148 * ln_persist) blocks = 148 * ln_persist;
   switch (C / 32) {
 #define OVG_LN_CASE(V) \
   case V: ovg::layernorm_kernel<V><<<blocks, ln_threads, 0, st>>>(p); break;

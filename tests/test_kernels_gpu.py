@@ -148,6 +148,27 @@ def test_attention_peaky_rows_rescale():
     assert rel(out, ref) < 1.5e-2, rel(out, ref)
 
 
+@pytest.mark.parametrize("spike_at", [130, 650, 699])
+def test_attention_late_spike_overflow(spike_at):
+    """One key far down the sequence whose logit exceeds everything before it by > 2^128: exp2 against the stale
+    reference overflows, the kernel must redo that step against the new maximum (and keep earlier / later steps exact)."""
+    ops = _ops()
+    batch, heads, n = 1, 2, 700
+    q = randn(batch, heads, n, 64, seed=1) * 0.3 + 2.0
+    k = randn(batch, heads, n, 64, seed=2) * 0.3
+    k[:, :, spike_at, :] = 3.0                      # q . k ~ 3 * 128 = 384 (log2 units: q is used unscaled)
+    k[:, 1, 5, :] = 1.0                             # head 1 additionally has a moderate early peak
+    v = randn(batch, heads, n, 64, seed=3)
+    qs, kb, vb = q.to(BF16), k.to(BF16), v.to(BF16)
+    out = torch.zeros(batch, n, heads * 64, device="cuda", dtype=BF16)
+    ops.attention(qs, kb, vb, out, batch, heads, n)
+    s = (qs.double() * math.log(2.0)) @ kb.double().transpose(-1, -2)
+    ref = (s.softmax(-1) @ vb.double()).transpose(1, 2).reshape(batch, n, heads * 64).float()
+    torch.cuda.synchronize()
+    assert torch.isfinite(out.float()).all()
+    assert rel(out, ref) < 1.5e-2, rel(out, ref)
+
+
 # ----------------------------------------------------------------------------------------------- LayerNorm & co
 @pytest.mark.parametrize("C", [128, 256, 1024, 2048])
 def test_layernorm(C):

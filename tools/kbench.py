@@ -47,6 +47,8 @@ for name, N, K, bns in () if KB == "attn" else (("qkv", 3072, 1024, (256, 512)),
             ms = timeit(lambda: ops.linear_resid(x, w, bias, gamma, xres, block_n=bn))
         elif name == "fc1":
             ms = timeit(lambda: ops.linear_bf16(x, w, bias, act=ops.L.ACT_GELU, out=out, block_n=bn))
+            ms0 = timeit(lambda: ops.linear_bf16(x, w, bias, out=out, block_n=bn))
+            res[f"gemm_fc1_noact_bn{bn}"] = dict(ms=ms0, tflops=2 * M * N * K / ms0 / 1e9)
         else:
             ms = timeit(lambda: ops.linear_bf16(x, w, bias, out=out, block_n=bn))
         res[f"gemm_{name}_bn{bn}"] = dict(ms=ms, tflops=2 * M * N * K / ms / 1e9)
@@ -97,8 +99,31 @@ res["sdpa_global_torch"] = dict(ms=ms, tflops=4 * M * M * C / ms / 1e9)
 # layernorm
 x32 = torch.randn(M, C, device=dev)
 ln_out = torch.empty(M, C, device=dev, dtype=BF16)
-ms = timeit(lambda: ops.layernorm(x32, ln_out, torch.ones(C, device=dev), torch.zeros(C, device=dev)))
+ln_w, ln_b = torch.ones(C, device=dev), torch.zeros(C, device=dev)
+ms = timeit(lambda: ops.layernorm(x32, ln_out, ln_w, ln_b))
 res["layernorm"] = dict(ms=ms, gbs=M * C * 6 / ms / 1e6)
+
+
+def timeit_warm(fn, iters=20):
+    for _ in range(3):
+        fn()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(iters):
+        fn()
+    e.record()
+    torch.cuda.synchronize()
+    return s.elapsed_time(e) / iters
+
+
+g = torch.cuda.CUDAGraph()
+ops.layernorm(x32, ln_out, ln_w, ln_b)
+torch.cuda.synchronize()
+with torch.cuda.graph(g):
+    for _ in range(20):
+        ops.layernorm(x32, ln_out, ln_w, ln_b)
+ms = timeit_warm(g.replay, iters=5) / 20
+res["layernorm_warm_l2"] = dict(ms=ms, gbs=M * C * 6 / ms / 1e6)
 for k_, v_ in res.items():
     print(k_, json.dumps(v_))
 os.makedirs("gpurun_out", exist_ok=True)
