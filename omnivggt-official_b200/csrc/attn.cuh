@@ -4,7 +4,10 @@
 //
 // q is pre-scaled by (1/sqrt(64))*log2(e) in the QKV GEMM epilogue, so probabilities are exp2(s - m).
 //
-// CTA = 256 query rows (two 128-row tiles, ping-pong) of one (batch, head).  Roles:
+// Two kernels share the per-tile algorithm:
+//   attn1_kernel (default, end of this file): CTA = 128 query rows of one (batch, head), 256 threads, two CTAs per SM.
+//   attn2_kernel: CTA = 256 query rows as two 128-row tiles, 384 threads, one CTA per SM (OVG_ATTN_SINGLE=0).
+// Roles in attn2_kernel (attn1_kernel is the same with one tile):
 //   warp 0        TMA producer: Q tiles once, K/V tiles through a 4-stage ring
 //   warps 1,2     MMA issuers (one per query tile): S_t = Q_t K^T (SS, M128 N128 K64) and O_t += P_t V (TS: P from TMEM,
 //                               V as MN-major smem operand, M128 N64 K128); issue order S_t(j+1), PV_t(j)
@@ -14,8 +17,10 @@
 // TMEM (512 cols): S0 [0,128) S1 [128,256) P0 [256,320) P1 [320,384) O0 [384,448) O1 [448,512).  P is separate from S so
 // that S_t(j+1) can be issued as soon as the softmax warps have S_t(j) in registers (barrier s_taken): the tensor pipe
 // then runs under the exp phase and each softmax warpgroup goes from one KV tile straight into the next.
-// Online softmax with lazy rescaling: O/l are rescaled only when the running max grows by > 8 (log2 units),
-// which is exact (the stale max cancels in O/l) and keeps P <= 256.
+// Online softmax with a stale reference and lazy rescaling: P(j) = exp2(S - m_ref) is computed against the reference of
+// the earlier steps while this step's row maximum is gathered in the same pass; O / l are rescaled (and the step redone
+// from the S row still in registers) only when the maximum exceeds the reference by > 8 (log2 units) -- exact, the stale
+// reference cancels in O / l, and P stays <= 256.
 #pragma once
 #include "ptx.cuh"
 
@@ -64,9 +69,6 @@ __device__ __forceinline__ float2 exp2_poly2(float2 x) {
   o.y = __int_as_float(__float_as_int(t.y) * 8388608 + __float_as_int(p.y));
   return o;
 }
-#ifndef OVG_ATT_TOKEN
-#define OVG_ATT_TOKEN 0     // 1: alternate the exp phases of the two query tiles with a token (measured: no gain, 717 vs 694 us)
-#endif
 #ifndef OVG_ATT_EMU_PAIRS
 #define OVG_ATT_EMU_PAIRS 4   // of every 16 element pairs, how many take the polynomial path (0 = all MUFU); 4 measured best
 #endif
@@ -76,14 +78,11 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
-// HALF = false: 8 softmax warps, one thread per query row (384 threads).
-// HALF = true : 16 softmax warps, two threads per query row (64 key columns each, 640 threads): four softmax warps per SM
-//               sub-partition instead of two, so the fixed per-step latencies of one warp (barrier round trips, TMEM
-//               load/store waits: ~500 of ~2500 clk) are covered by the exp phases of three others.
-constexpr int ATT_THREADS_HALF = 640;
-template <bool HALF>
-__global__ void __launch_bounds__(HALF ? ATT_THREADS_HALF : ATT_THREADS, 1)
-attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+// Paired kernel: CTA = 256 query rows as two 128-row tiles, 8 softmax warps (one thread per query row), 384 threads,
+// one CTA per SM.  Kept selectable (OVG_ATTN_SINGLE=0); the single-tile kernel at the end of this file is the default.
+// (A 16-warp variant with two threads per query row was measured slower -- 760 vs 694 us -- and removed.)
+__global__ void __launch_bounds__(ATT_THREADS, 1)
+attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
             const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
   constexpr int NS = ATT_KV_STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -102,8 +101,6 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
   uint64_t* o_ready = p_full + 2;      // [2]
   uint64_t* s_taken = o_ready + 2;     // [2]  softmax has the S tile in registers -> S buffer may be overwritten
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_taken + 2);
-  uint64_t* mufu_tok = s_taken + 2 + 1;   // [2 tiles][4 SM sub-partitions] (slot after tmem_slot's 8 bytes)
-  float* s_xch = reinterpret_cast<float*>(bars + 64);   // HALF: [2 slots][2 tiles][2 halves][128 rows] row-max / row-sum exchange
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -120,11 +117,10 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
     for (int i = 0; i < 2; ++i) {
       mbar_init(&q_full[i], 1);
       mbar_init(&s_full[i], 1);
-      mbar_init(&p_full[i], HALF ? 8 : 4);
+      mbar_init(&p_full[i], 4);
       mbar_init(&o_ready[i], 1);
-      mbar_init(&s_taken[i], HALF ? 8 : 4);
+      mbar_init(&s_taken[i], 4);
     }
-    for (int i = 0; i < 8; ++i) mbar_init(&mufu_tok[i], 1);
     for (int i = 0; i < NS; ++i) {
       mbar_init(&k_full[i], 1);
       mbar_init(&k_empty[i], two ? 2 : 1);   // one commit per MMA issuer (tile)
@@ -143,9 +139,8 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
   const uint32_t tmem_base = *tmem_slot;
 
   // register budget after the split must stay <= the launch allocation: 168 * 384 = 64512 (128*72 + 256*208 = 62464);
-  // HALF: 96 * 640 = 61440 (128*56 + 512*104 = 60416)
   if (warp < 4) {
-    if constexpr (HALF) reg_dealloc<56>(); else reg_dealloc<72>();
+    reg_dealloc<72>();
   }
   if (warp == 0) {
     if (lane == 0) {
@@ -225,121 +220,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
       }
     }
   } else if (warp >= 4) {
-    if constexpr (HALF) {
-      reg_alloc<104>();
-      const int sw = warp - 4;               // 0..15
-      const int t = sw >> 3;                 // query tile
-      if (t == 0 || two) {
-        const int quarter = warp & 3;        // TMEM lane quarter (hardware: 32 * (warp % 4))
-        const int half = (sw >> 2) & 1;      // key columns [64*half, 64*half + 64) of every S tile
-        const int r = quarter * 32 + lane;
-        const int qrow = q0 + t * 128 + r;
-        const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
-        const uint32_t tS = tmem_base + t * 128 + half * 64 + lane_off;
-        const uint32_t tP = tmem_base + 256 + t * 64 + half * 32 + lane_off;
-        const uint32_t tO = tmem_base + 384 + t * 64 + half * 32 + lane_off;
-        const int bar_id = 1 + t * 4 + quarter;      // named barrier shared by the two warps that own the same rows
-        float m_used = -INFINITY;
-        float l = 0.f;
-        for (int j = 0; j < nkv; ++j) {
-          const int kv_valid = min(128, p.n - j * 128) - half * 64;   // valid columns of this half (may be <= 0)
-          mbar_wait(&s_full[t], j & 1);
-          tc_fence_after();
-          uint32_t raw[64];
-          tmem_ld32(tS, raw);
-          tmem_ld32(tS + 32, raw + 32);
-          tmem_ld_wait();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&s_taken[t]);
-          if (kv_valid < 64) {
-#pragma unroll
-            for (int i = 0; i < 64; ++i)
-              if (i >= kv_valid) raw[i] = 0xff800000u;
-          }
-          float mx0 = -INFINITY, mx1 = -INFINITY;
-#pragma unroll
-          for (int i = 0; i < 64; i += 4) {
-            mx0 = fmaxf(fmaxf(mx0, __uint_as_float(raw[i])), __uint_as_float(raw[i + 1]));
-            mx1 = fmaxf(fmaxf(mx1, __uint_as_float(raw[i + 2])), __uint_as_float(raw[i + 3]));
-          }
-          // row max = max over both halves: exchange through smem (double-buffered by step parity)
-          float* xs = s_xch + (((j & 1) * 2 + t) * 2) * 128;
-          xs[half * 128 + r] = fmaxf(mx0, mx1);
-          asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
-          const float m_new = fmaxf(m_used, fmaxf(xs[r], xs[128 + r]));
-          if (j == 0) {
-            m_used = m_new;
-          } else {
-            mbar_wait(&o_ready[t], (j - 1) & 1);     // PV(j-1) done: O stable, P buffer reusable
-            tc_fence_after();
-            const bool need = (m_new - m_used) > 8.0f;       // identical in both halves (same inputs)
-            if (__any_sync(0xffffffffu, need)) {
-              const float alpha = need ? ex2_approx(m_used - m_new) : 1.0f;
-              if (need) {
-                m_used = m_new;
-                l *= alpha;
-              }
-              uint32_t o[32];
-              tmem_ld32(tO, o);
-              tmem_ld_wait();
-#pragma unroll
-              for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-              tmem_st32(tO, o);
-              tmem_st_wait();
-            }
-          }
-          const float2 negm = make_float2(-m_used, -m_used);
-          float2 acc = make_float2(0.f, 0.f);
-#pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            uint32_t pk[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              float2 x = make_float2(__uint_as_float(raw[c * 32 + 2 * i]), __uint_as_float(raw[c * 32 + 2 * i + 1]));
-              x = fadd2(x, negm);
-              if (i >= 16 - OVG_ATT_EMU_PAIRS) {
-                x = exp2_poly2(x);
-              } else {
-                x.x = ex2_approx(x.x);
-                x.y = ex2_approx(x.y);
-              }
-              acc = fadd2(acc, x);
-              pk[i] = pack_bf16(x.x, x.y);
-            }
-            tmem_st16(tP + c * 16, pk);
-          }
-          l += acc.x + acc.y;
-          tmem_st_wait();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&p_full[t]);
-        }
-        // ---- epilogue: l = l_half0 + l_half1; this thread writes 32 of the row's 64 output columns
-        float* xs = s_xch + (((nkv & 1) * 2 + t) * 2) * 128;
-        xs[half * 128 + r] = l;
-        asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
-        const float inv = 1.0f / (xs[r] + xs[128 + r]);
-        mbar_wait(&o_ready[t], (nkv - 1) & 1);
-        tc_fence_after();
-        uint32_t o[32];
-        tmem_ld32(tO, o);
-        tmem_ld_wait();
-        if (qrow < p.n) {
-          uint4* dst = reinterpret_cast<uint4*>(p.out + (static_cast<long long>(blockIdx.z) * p.n + qrow) * p.C +
-                                                head * 64 + half * 32);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            uint4 w;
-            w.x = pack_bf16(__uint_as_float(o[8 * i + 0]) * inv, __uint_as_float(o[8 * i + 1]) * inv);
-            w.y = pack_bf16(__uint_as_float(o[8 * i + 2]) * inv, __uint_as_float(o[8 * i + 3]) * inv);
-            w.z = pack_bf16(__uint_as_float(o[8 * i + 4]) * inv, __uint_as_float(o[8 * i + 5]) * inv);
-            w.w = pack_bf16(__uint_as_float(o[8 * i + 6]) * inv, __uint_as_float(o[8 * i + 7]) * inv);
-            dst[i] = w;
-          }
-        }
-      }
-    } else {
+    {
     reg_alloc<208>();
       const int t = (warp - 4) >> 2;
       if (t == 0 || two) {
@@ -513,6 +394,289 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Single-tile variant: CTA = 128 query rows, 256 threads, TWO CTAs per SM (256 TMEM columns, ~112 KB smem and half of
+// the register file each).  Same per-tile algorithm as attn2_kernel, but the two tiles that share an SM are
+// independent CTAs: their phases drift freely, one CTA's prologue (barrier init, TMEM alloc, Q / first K loads) and
+// epilogue (O read-out, global stores, TMEM free) run under the other CTA's main loop, and the grid quantises in
+// 128-row units.  Cost: every CTA streams K/V for itself (2x the L2->SM bytes of the paired kernel).
+//   warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2-3 idle, warps 4-7 softmax (one query row per thread).
+// TMEM (256 cols): S [0,128) P [128,192) O [192,256).
+constexpr int ATT1_THREADS = 256;
+constexpr int ATT1_KV_STAGES = 3;
+constexpr int ATT1_SMEM_BYTES = (1 + 2 * ATT1_KV_STAGES) * ATT_TILE_BYTES + 256;   // base must be 1024-aligned (checked)
+
+__global__ void __launch_bounds__(ATT1_THREADS, 2)
+attn1_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+             const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+  constexpr int NS = ATT1_KV_STAGES;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sQ = smem;
+  uint8_t* sK = smem + ATT_TILE_BYTES;
+  uint8_t* sV = sK + NS * ATT_TILE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + NS * ATT_TILE_BYTES);
+  uint64_t* q_full = bars;             // [1]
+  uint64_t* k_full = bars + 1;         // [NS]
+  uint64_t* k_empty = k_full + NS;     // [NS]
+  uint64_t* v_full = k_empty + NS;     // [NS]
+  uint64_t* v_empty = v_full + NS;     // [NS]
+  uint64_t* s_full = v_empty + NS;     // [1]
+  uint64_t* p_full = s_full + 1;       // [1]
+  uint64_t* o_ready = p_full + 1;      // [1]
+  uint64_t* s_taken = o_ready + 1;     // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_taken + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 128;
+  const int head = blockIdx.y;
+  const int bh = blockIdx.z * p.heads + head;
+  const int nkv = (p.n + 127) / 128;
+
+  if (warp == 0 && lane == 0) {
+    if (smem_u32(smem) & 1023u) {
+      printf("ovg attn1: dynamic shared memory base is not 1024-byte aligned\n");
+      __trap();
+    }
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    mbar_init(q_full, 1);
+    mbar_init(s_full, 1);
+    mbar_init(p_full, 4);
+    mbar_init(o_ready, 1);
+    mbar_init(s_taken, 4);
+    for (int i = 0; i < NS; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // register budget: launch allocation 128 * 256 = 32768 per CTA; after the split 128*40 + 128*208 = 31744
+  if (warp < 4) reg_dealloc<40>();
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(q_full, ATT_TILE_BYTES);
+      tma_load_3d(sQ, &tmQ, q_full, 0, q0, bh);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int j = 0; j < nkv; ++j) {
+        mbar_wait(&k_empty[s], ph ^ 1);
+        mbar_expect_tx(&k_full[s], ATT_TILE_BYTES);
+        tma_load_3d(sK + s * ATT_TILE_BYTES, &tmK, &k_full[s], 0, j * 128, bh);
+        mbar_wait(&v_empty[s], ph ^ 1);
+        mbar_expect_tx(&v_full[s], ATT_TILE_BYTES);
+        tma_load_3d(sV + s * ATT_TILE_BYTES, &tmV, &v_full[s], 0, j * 128, bh);
+        if (++s == NS) {
+          s = 0;
+          ph ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
+      constexpr uint32_t idesc_pv = make_idesc_bf16(128, 64, 0, 1);  // B (=V) is MN-major
+      const uint32_t tS = tmem_base;
+      const uint32_t tP = tmem_base + 128;
+      const uint32_t tO = tmem_base + 192;
+      const uint64_t qdesc = make_sw128_desc(smem_u32(sQ));
+      const uint64_t kdesc0 = make_sw128_desc(smem_u32(sK));
+      const uint64_t vdesc0 = make_sw128_desc(smem_u32(sV));
+      constexpr uint64_t kStageStep = ATT_TILE_BYTES >> 4;
+      auto issue_S = [&](int stage) {
+        const uint64_t bdesc = kdesc0 + stage * kStageStep;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_ss(tS, qdesc + 2 * k, bdesc + 2 * k, idesc_s, k > 0 ? 1u : 0u);
+        umma_commit(s_full);
+      };
+      auto issue_PV = [&](int stage, int j) {
+        const uint64_t bdesc = vdesc0 + stage * kStageStep;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          umma_ts(tO, tP + 8 * k, bdesc + static_cast<uint64_t>(k) * (2048 >> 4), idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
+        umma_commit(o_ready);
+      };
+      mbar_wait(q_full, 0);
+      mbar_wait(&k_full[0], 0);
+      tc_fence_after();
+      issue_S(0);
+      umma_commit(&k_empty[0]);
+      int s = 0, sn = 1 % NS;
+      uint32_t ph = 0, phn = (NS == 1) ? 1u : 0u;
+      for (int j = 0; j < nkv; ++j) {
+        if (j + 1 < nkv) {              // S(j+1) as soon as the softmax warps hold S(j) in registers
+          mbar_wait(&k_full[sn], phn);
+          mbar_wait(s_taken, j & 1);
+          tc_fence_after();
+          issue_S(sn);
+          umma_commit(&k_empty[sn]);
+        }
+        mbar_wait(&v_full[s], ph);
+        mbar_wait(p_full, j & 1);
+        tc_fence_after();
+        issue_PV(s, j);
+        umma_commit(&v_empty[s]);
+        s = sn;
+        ph = phn;
+        if (++sn == NS) {
+          sn = 0;
+          phn ^= 1;
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    reg_alloc<208>();
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const int qrow = q0 + r;
+    const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
+    const uint32_t tS = tmem_base + lane_off;
+    const uint32_t tP = tmem_base + 128 + lane_off;
+    const uint32_t tO = tmem_base + 192 + lane_off;
+    float m_used = -INFINITY;
+    float l = 0.f;
+    for (int j = 0; j < nkv; ++j) {
+      const int kv_valid = min(128, p.n - j * 128);
+      mbar_wait(s_full, j & 1);
+      tc_fence_after();
+      uint32_t raw[128];
+      tmem_ld32(tS, raw);
+      tmem_ld32(tS + 32, raw + 32);
+      tmem_ld32(tS + 64, raw + 64);
+      tmem_ld32(tS + 96, raw + 96);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_taken);
+      if (kv_valid != 128) {
+#pragma unroll
+        for (int i = 0; i < 128; ++i)
+          if (i >= kv_valid) raw[i] = 0xff800000u;
+      }
+      // stale-reference softmax step, see attn2_kernel
+      float2 acc = make_float2(0.f, 0.f);
+      bool slow = (j == 0);
+      float m_new = m_used;
+      if (j > 0) {
+        const float2 negm = make_float2(-m_used, -m_used);
+        float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float r0 = __uint_as_float(raw[c * 32 + 2 * i]), r1 = __uint_as_float(raw[c * 32 + 2 * i + 1]);
+            if (i & 1) mx1 = fmaxf(fmaxf(mx1, r0), r1); else mx0 = fmaxf(fmaxf(mx0, r0), r1);
+            float2 x = fadd2(make_float2(r0, r1), negm);
+            if (i >= 16 - OVG_ATT_EMU_PAIRS) {
+              x = exp2_poly2(x);
+            } else {
+              x.x = ex2_approx(x.x);
+              x.y = ex2_approx(x.y);
+            }
+            acc = fadd2(acc, x);
+            pk[i] = pack_bf16(x.x, x.y);
+          }
+          if (c == 0) {
+            mbar_wait(o_ready, (j - 1) & 1);   // PV(j-1) complete: P buffer reusable, O stable
+            tc_fence_after();
+          }
+          tmem_st16(tP + c * 16, pk);
+        }
+        m_new = fmaxf(m_used, fmaxf(mx0, mx1));
+        slow = __any_sync(0xffffffffu, (m_new - m_used) > 8.0f);
+      }
+      if (slow) {
+        if (j == 0) {
+          float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+          for (int i = 0; i < 128; i += 4) {
+            mx0 = fmaxf(fmaxf(mx0, __uint_as_float(raw[i])), __uint_as_float(raw[i + 1]));
+            mx1 = fmaxf(fmaxf(mx1, __uint_as_float(raw[i + 2])), __uint_as_float(raw[i + 3]));
+          }
+          m_used = fmaxf(mx0, mx1);
+        } else {
+          const bool need = (m_new - m_used) > 8.0f;
+          const float alpha = need ? ex2_approx(m_used - m_new) : 1.0f;
+          if (need) {
+            m_used = m_new;
+            l *= alpha;
+          }
+          tmem_st_wait();
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            uint32_t o[32];
+            tmem_ld32(tO + c * 32, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st32(tO + c * 32, o);
+          }
+        }
+        const float2 negm = make_float2(-m_used, -m_used);
+        acc = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float2 x = make_float2(__uint_as_float(raw[c * 32 + 2 * i]), __uint_as_float(raw[c * 32 + 2 * i + 1]));
+            x = fadd2(x, negm);
+            x.x = ex2_approx(x.x);
+            x.y = ex2_approx(x.y);
+            acc = fadd2(acc, x);
+            pk[i] = pack_bf16(x.x, x.y);
+          }
+          tmem_st16(tP + c * 16, pk);
+        }
+      }
+      l += acc.x + acc.y;
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+    }
+    // ---- epilogue: O / l -> bf16 -> out[b, qrow, head*64 .. +64)
+    mbar_wait(o_ready, (nkv - 1) & 1);
+    tc_fence_after();
+    const float inv = 1.0f / l;
+    uint32_t o[64];
+    tmem_ld32(tO, o);
+    tmem_ld32(tO + 32, o + 32);
+    tmem_ld_wait();
+    if (qrow < p.n) {
+      uint4* dst = reinterpret_cast<uint4*>(p.out + (static_cast<long long>(blockIdx.z) * p.n + qrow) * p.C + head * 64);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        uint4 w;
+        w.x = pack_bf16(__uint_as_float(o[8 * i + 0]) * inv, __uint_as_float(o[8 * i + 1]) * inv);
+        w.y = pack_bf16(__uint_as_float(o[8 * i + 2]) * inv, __uint_as_float(o[8 * i + 3]) * inv);
+        w.z = pack_bf16(__uint_as_float(o[8 * i + 4]) * inv, __uint_as_float(o[8 * i + 5]) * inv);
+        w.w = pack_bf16(__uint_as_float(o[8 * i + 6]) * inv, __uint_as_float(o[8 * i + 7]) * inv);
+        dst[i] = w;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
   }
 }
 

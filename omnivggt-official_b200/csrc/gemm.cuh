@@ -67,13 +67,14 @@ constexpr int GEMM_BK = 64;
 constexpr int GEMM_THREADS = 320;
 constexpr int GEMM_A_BYTES = GEMM_BM * GEMM_BK * 2;
 
+constexpr int GEMM_QKV_TABLE_BYTES = 3 * 64 * 18 * 4 + 1024;   // QKV epilogue: rope cos / sin / -sin + q,k LayerNorm affine
 template <int BN>
 struct GemmCfg {
   static constexpr int B_BYTES = BN * GEMM_BK * 2;
   static constexpr int STAGE_BYTES = GEMM_A_BYTES + B_BYTES;
   static constexpr int STAGES = (BN >= 256) ? 4 : (BN >= 128 ? 6 : 8);
   static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 2 * 64 * 17 * 4;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + GEMM_QKV_TABLE_BYTES;
 };
 
 // Exact-erf GELU (nn.GELU() default, reference layers/mlp.py:22,:36) with erf evaluated by Abramowitz-Stegun 7.1.26
@@ -123,7 +124,8 @@ __device__ __forceinline__ float2 gelu_erf2(const float2 x) {
 template <int BN, int EPI>
 __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const uint32_t trow, const int m, const int n0,
                                               const int colhalf, const float* s_rope, uint8_t* stg = nullptr,
-                                              const CUtensorMap* tmO = nullptr) {
+                                              const CUtensorMap* tmO = nullptr, const CUtensorMap* tmO2 = nullptr,
+                                              const CUtensorMap* tmO3 = nullptr) {
   if constexpr (EPI == EPI_QKV) {
     // ---- per-row RoPE position (reference omnivggt_aggregator.py:215-224; layers/rope.py:39-59)
     int py = 0, px = 0;
@@ -135,10 +137,15 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const uint32_
         px = pp % p.wp + 1;
       }
     }
-    const float* cy = s_rope + py * 17;
-    const float* sy = s_rope + 64 * 17 + py * 17;
-    const float* cx = s_rope + px * 17;
-    const float* sx = s_rope + 64 * 17 + px * 17;
+    // smem tables (filled at kernel start): [cos | sin | -sin][64 positions][18] (16 frequencies, rows padded to 18
+    // floats so that float2 reads stay aligned), then the q / k LayerNorm affine [qw*qscale | qb*qscale | kw | kb][64].
+    const float2* cy = reinterpret_cast<const float2*>(s_rope + py * 18);
+    const float2* sy = reinterpret_cast<const float2*>(s_rope + 64 * 18 + py * 18);
+    const float2* nsy = reinterpret_cast<const float2*>(s_rope + 128 * 18 + py * 18);
+    const float2* cx = reinterpret_cast<const float2*>(s_rope + px * 18);
+    const float2* sx = reinterpret_cast<const float2*>(s_rope + 64 * 18 + px * 18);
+    const float2* nsx = reinterpret_cast<const float2*>(s_rope + 128 * 18 + px * 18);
+    const float* s_ln = s_rope + 3 * 64 * 18;
     const long long seq = m / p.ntok;
     const long long tok = m % p.ntok;
     const int heads = p.C >> 6;
@@ -148,80 +155,110 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const uint32_
       tmem_ld32(trow + c * 64, raw);
       tmem_ld32(trow + c * 64 + 32, raw + 32);
       tmem_ld_wait();
-      if (m < p.M && n < p.N) {
-        float v[64];
+      if (n >= p.N || m - static_cast<int>(threadIdx.x & 31) >= p.M) continue;   // warp-uniform
+      const long long tok0 = __shfl_sync(0xffffffffu, tok, 0);   // all 32 lanes are converged here
+      if (p.staged || m < p.M) {                               // staged: every lane of the warp takes part
+        // all arithmetic on packed fp32 pairs (FADD2 / FMUL2 / FFMA2): v2[i] = elements (2i, 2i+1) of this head
+        float2 v2[32];
         {
           const float4* b4 = reinterpret_cast<const float4*>(p.bias + n);
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const float4 b = __ldg(b4 + i);
-            v[4 * i + 0] = __uint_as_float(raw[4 * i + 0]) + b.x;
-            v[4 * i + 1] = __uint_as_float(raw[4 * i + 1]) + b.y;
-            v[4 * i + 2] = __uint_as_float(raw[4 * i + 2]) + b.z;
-            v[4 * i + 3] = __uint_as_float(raw[4 * i + 3]) + b.w;
+            v2[2 * i] = fadd2(make_float2(__uint_as_float(raw[4 * i + 0]), __uint_as_float(raw[4 * i + 1])), make_float2(b.x, b.y));
+            v2[2 * i + 1] = fadd2(make_float2(__uint_as_float(raw[4 * i + 2]), __uint_as_float(raw[4 * i + 3])), make_float2(b.z, b.w));
           }
         }
         const int which = n / p.C;
         const int h = (n - which * p.C) >> 6;
         if (which < 2 && p.qk_norm) {
-          const float* w = which == 0 ? p.qn_w : p.kn_w;
-          const float* b = which == 0 ? p.qn_b : p.kn_b;
-          // four independent partial sums: a single serial fp32 chain of 64 adds is ~256 clk of pure latency
-          float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+          float2 s01 = make_float2(0.f, 0.f), s23 = make_float2(0.f, 0.f);
 #pragma unroll
-          for (int i = 0; i < 64; i += 4) {
-            s0 += v[i];
-            s1 += v[i + 1];
-            s2 += v[i + 2];
-            s3 += v[i + 3];
+          for (int i = 0; i < 32; i += 2) {
+            s01 = fadd2(s01, v2[i]);
+            s23 = fadd2(s23, v2[i + 1]);
           }
-          const float mean = ((s0 + s1) + (s2 + s3)) * (1.0f / 64.0f);
-          float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+          const float mean = ((s01.x + s01.y) + (s23.x + s23.y)) * (1.0f / 64.0f);
+          const float2 nm = make_float2(-mean, -mean);
+          float2 q01 = make_float2(0.f, 0.f), q23 = make_float2(0.f, 0.f);
 #pragma unroll
-          for (int i = 0; i < 64; i += 4) {
-            const float d0 = v[i] - mean, d1 = v[i + 1] - mean, d2 = v[i + 2] - mean, d3 = v[i + 3] - mean;
-            q0 = fmaf(d0, d0, q0);
-            q1 = fmaf(d1, d1, q1);
-            q2 = fmaf(d2, d2, q2);
-            q3 = fmaf(d3, d3, q3);
+          for (int i = 0; i < 32; i += 2) {
+            v2[i] = fadd2(v2[i], nm);
+            v2[i + 1] = fadd2(v2[i + 1], nm);
+            q01 = ffma2(v2[i], v2[i], q01);
+            q23 = ffma2(v2[i + 1], v2[i + 1], q23);
           }
-          const float rstd = rsqrtf(((q0 + q1) + (q2 + q3)) * (1.0f / 64.0f) + 1e-5f);
+          const float rstd = rsqrtf(((q01.x + q01.y) + (q23.x + q23.y)) * (1.0f / 64.0f) + 1e-5f);
+          const float2 rr = make_float2(rstd, rstd);
+          const float4* w4 = reinterpret_cast<const float4*>(s_ln + which * 128);        // q: pre-multiplied by qscale
+          const float4* b4 = reinterpret_cast<const float4*>(s_ln + which * 128 + 64);
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            const float4 w4 = __ldg(reinterpret_cast<const float4*>(w) + i);
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(b) + i);
-            v[4 * i + 0] = (v[4 * i + 0] - mean) * rstd * w4.x + b4.x;
-            v[4 * i + 1] = (v[4 * i + 1] - mean) * rstd * w4.y + b4.y;
-            v[4 * i + 2] = (v[4 * i + 2] - mean) * rstd * w4.z + b4.z;
-            v[4 * i + 3] = (v[4 * i + 3] - mean) * rstd * w4.w + b4.w;
+            const float4 w = w4[i];
+            const float4 b = b4[i];
+            v2[2 * i] = ffma2(fmul2(v2[2 * i], rr), make_float2(w.x, w.y), make_float2(b.x, b.y));
+            v2[2 * i + 1] = ffma2(fmul2(v2[2 * i + 1], rr), make_float2(w.z, w.w), make_float2(b.z, b.w));
           }
+        } else if (which == 0) {
+          const float2 qs = make_float2(p.qscale, p.qscale);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v2[i] = fmul2(v2[i], qs);
         }
         if (which < 2 && p.rope) {
+          // rotate (d, d+16) with the row angle and (32+d, 48+d) with the column angle (layers/rope.py:154-188)
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float a0 = v[i], b0 = v[i + 16];
-            v[i] = a0 * cy[i] - b0 * sy[i];
-            v[i + 16] = b0 * cy[i] + a0 * sy[i];
-            const float a1 = v[32 + i], b1 = v[48 + i];
-            v[32 + i] = a1 * cx[i] - b1 * sx[i];
-            v[48 + i] = b1 * cx[i] + a1 * sx[i];
+          for (int k = 0; k < 8; ++k) {
+            const float2 a0 = v2[k], b0 = v2[8 + k];
+            v2[k] = ffma2(b0, nsy[k], fmul2(a0, cy[k]));
+            v2[8 + k] = ffma2(a0, sy[k], fmul2(b0, cy[k]));
+            const float2 a1 = v2[16 + k], b1 = v2[24 + k];
+            v2[16 + k] = ffma2(b1, nsx[k], fmul2(a1, cx[k]));
+            v2[24 + k] = ffma2(a1, sx[k], fmul2(b1, cx[k]));
           }
         }
-        if (which == 0) {
+        // 32 rows x 128 B (one head of 32 tokens) -> 128B-swizzled smem tile -> one bulk tensor store into the
+        // head-major [batch*heads, ntok, 64] output.  Direct stores (every lane a different 128 B row) kept the LSU
+        // busy for ~20% of the kernel.  The few warps whose 32 rows straddle two sequences (or the end of the problem)
+        // keep the direct path: a second bulk store at a negative token coordinate faults on sm_100.
+        if (p.staged && tok0 + 32 <= p.ntok) {
+          const int lane = threadIdx.x & 31;
+          if (lane == 0) tma_store_wait_read0();
+          __syncwarp();
 #pragma unroll
-          for (int i = 0; i < 64; ++i) v[i] *= p.qscale;
+          for (int i = 0; i < 8; ++i) {
+            uint4 o;
+            o.x = pack_bf16(v2[4 * i + 0].x, v2[4 * i + 0].y);
+            o.y = pack_bf16(v2[4 * i + 1].x, v2[4 * i + 1].y);
+            o.z = pack_bf16(v2[4 * i + 2].x, v2[4 * i + 2].y);
+            o.w = pack_bf16(v2[4 * i + 3].x, v2[4 * i + 3].y);
+            *reinterpret_cast<uint4*>(stg + lane * 128 + ((i ^ (lane & 7)) << 4)) = o;
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            const CUtensorMap* tm = which == 0 ? tmO : (which == 1 ? tmO2 : tmO3);
+            const int bh = static_cast<int>(seq) * heads + h;     // lane 0: seq / tok of the warp's first row
+            tma_store_3d(tm, stg, 0, static_cast<int>(tok), bh);
+            tma_store_commit();
+          }
+          continue;
         }
+        if (m >= p.M) continue;
         __nv_bfloat16* dst = (which == 0 ? p.q_out : (which == 1 ? p.k_out : p.v_out)) +
                              ((seq * heads + h) * p.ntok + tok) * 64;
         uint4* d4 = reinterpret_cast<uint4*>(dst);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           uint4 o;
-          o.x = pack_bf16(v[8 * i + 0], v[8 * i + 1]);
-          o.y = pack_bf16(v[8 * i + 2], v[8 * i + 3]);
-          o.z = pack_bf16(v[8 * i + 4], v[8 * i + 5]);
-          o.w = pack_bf16(v[8 * i + 6], v[8 * i + 7]);
+          o.x = pack_bf16(v2[4 * i + 0].x, v2[4 * i + 0].y);
+          o.y = pack_bf16(v2[4 * i + 1].x, v2[4 * i + 1].y);
+          o.z = pack_bf16(v2[4 * i + 2].x, v2[4 * i + 2].y);
+          o.w = pack_bf16(v2[4 * i + 3].x, v2[4 * i + 3].y);
+#ifdef OVG_QKV_NOSTORE
+          if (o.x == 0x12345678u) d4[i] = o;
+#else
           d4[i] = o;
+#endif
         }
       }
     }
@@ -430,7 +467,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   uint64_t* tfull = bars + 2 * STAGES;
   uint64_t* tempty = bars + 2 * STAGES + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
-  float* s_rope = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES + 256);  // [2][maxpos][17]
+  float* s_rope = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES + 256);  // [3][64][18] + [4][64]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -457,8 +494,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   }
   if (EPI == EPI_QKV && warp >= 2) {
     for (int i = threadIdx.x - 64; i < p.maxpos * 16; i += GEMM_THREADS - 64) {
-      s_rope[(i >> 4) * 17 + (i & 15)] = p.rope_cos[i];
-      s_rope[64 * 17 + (i >> 4) * 17 + (i & 15)] = p.rope_sin[i];
+      s_rope[(i >> 4) * 18 + (i & 15)] = p.rope_cos[i];
+      s_rope[64 * 18 + (i >> 4) * 18 + (i & 15)] = p.rope_sin[i];
+      s_rope[128 * 18 + (i >> 4) * 18 + (i & 15)] = -p.rope_sin[i];
+    }
+    if (p.qk_norm && threadIdx.x >= 64 && threadIdx.x < 128) {
+      float* s_ln = s_rope + 3 * 64 * 18;
+      const int i = threadIdx.x - 64;
+      s_ln[i] = p.qn_w[i] * p.qscale;          // q is pre-scaled by log2(e)/sqrt(head_dim): fold it into the affine
+      s_ln[64 + i] = p.qn_b[i] * p.qscale;
+      s_ln[128 + i] = p.kn_w[i];
+      s_ln[192 + i] = p.kn_b[i];
     }
   }
   tc_fence_before();
@@ -563,19 +609,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 // 128 x 256 single-CTA tile needs ~87 FLOP per L2->SM byte and saturates the L2 fabric (~10-12 TB/s) near 1 PFLOP/s;
 // the paired tile needs 131 FLOP/B.  The pair leader issues M=256 MMAs that write both CTAs' TMEM; every CTA runs its own
 // TMA producer and epilogue (rows [128*rank, 128*rank+128) of the tile).
-constexpr int GEMM2_STG_BYTES = 8 * 4096;   // one 32 x 32 fp32 (or bf16) staging tile per epilogue warp; aliases the rope table
+constexpr int GEMM2_STG_BYTES = 8 * 4096;   // one 32 x 32 fp32 (or bf16) staging tile per epilogue warp; followed by the QKV tables
 template <int BN>
 struct Gemm2Cfg {
   static constexpr int STAGES = BN >= 256 ? 5 : 7;
   static constexpr int B_BYTES = (BN / 2) * GEMM_BK * 2;       // each CTA stages half of the B rows
   static constexpr int STAGE_BYTES = GEMM_A_BYTES + B_BYTES;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + 1024 + GEMM2_STG_BYTES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + 1024 + GEMM2_STG_BYTES + GEMM_QKV_TABLE_BYTES;
 };
 
 template <int BN, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-             const __grid_constant__ CUtensorMap tmO, const GemmParams p) {
+             const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmO2,
+             const __grid_constant__ CUtensorMap tmO3, const GemmParams p) {
   using Cfg2 = Gemm2Cfg<BN>;
   constexpr int STAGES = Cfg2::STAGES;
   constexpr int GEMM2_B_BYTES = Cfg2::B_BYTES;
@@ -591,7 +638,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   uint64_t* tempty = bars + 2 * STAGES + 2; // used in the leader only: 8 epilogue warps x 2 CTAs
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
   uint8_t* s_stage = smem + STAGES * GEMM2_STAGE_BYTES + 1024;     // 1024-aligned: swizzled TMA-store tiles
-  float* s_rope = reinterpret_cast<float*>(s_stage);                // QKV epilogue only (never staged)
+  float* s_rope = reinterpret_cast<float*>(s_stage + GEMM2_STG_BYTES);   // QKV epilogue tables
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -606,7 +653,13 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    if (p.staged) tma_prefetch_desc(&tmO);
+    if (p.staged) {
+      tma_prefetch_desc(&tmO);
+      if (EPI == EPI_QKV) {
+        tma_prefetch_desc(&tmO2);
+        tma_prefetch_desc(&tmO3);
+      }
+    }
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], 1);
@@ -623,8 +676,17 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   }
   if (EPI == EPI_QKV && warp >= 2) {
     for (int i = threadIdx.x - 64; i < p.maxpos * 16; i += GEMM_THREADS - 64) {
-      s_rope[(i >> 4) * 17 + (i & 15)] = p.rope_cos[i];
-      s_rope[64 * 17 + (i >> 4) * 17 + (i & 15)] = p.rope_sin[i];
+      s_rope[(i >> 4) * 18 + (i & 15)] = p.rope_cos[i];
+      s_rope[64 * 18 + (i >> 4) * 18 + (i & 15)] = p.rope_sin[i];
+      s_rope[128 * 18 + (i >> 4) * 18 + (i & 15)] = -p.rope_sin[i];
+    }
+    if (p.qk_norm && threadIdx.x >= 64 && threadIdx.x < 128) {
+      float* s_ln = s_rope + 3 * 64 * 18;
+      const int i = threadIdx.x - 64;
+      s_ln[i] = p.qn_w[i] * p.qscale;          // q is pre-scaled by log2(e)/sqrt(head_dim): fold it into the affine
+      s_ln[64 + i] = p.qn_b[i] * p.qscale;
+      s_ln[128 + i] = p.kn_w[i];
+      s_ln[192 + i] = p.kn_b[i];
     }
   }
   tc_fence_before();
@@ -704,7 +766,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       mbar_wait(&tfull[as], aph);
       tc_fence_after();
       const uint32_t trow = tmem_base + as * BN + (static_cast<uint32_t>(quarter * 32) << 16);
-      epilogue_tile<BN, EPI>(p, trow, m, n0, colhalf, s_rope, s_stage + (warp - 2) * 4096, &tmO);
+      epilogue_tile<BN, EPI>(p, trow, m, n0, colhalf, s_rope, s_stage + (warp - 2) * 4096, &tmO, &tmO2, &tmO3);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {

@@ -16,7 +16,6 @@ namespace {
 
 thread_local std::string g_err;
 std::atomic<long long> g_launches{0};
-const bool g_attn_half = [] { const char* e = getenv("OVG_ATTN_HALF"); return e && e[0] == '1'; }();   // A/B switch
 const bool g_stage_default = [] { const char* e = getenv("OVG_GEMM_STAGE"); return !(e && e[0] == '0'); }();   // A/B switch
 const bool g_pair_default = [] { const char* e = getenv("OVG_GEMM_PAIR"); return !(e && e[0] == '0'); }();   // A/B switch
 
@@ -169,7 +168,7 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const ovg::GemmPar
 }
 
 template <int BN, int EPI>
-int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const ovg::GemmParams& p,
+int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap (&to)[3], const ovg::GemmParams& p,
                  cudaStream_t st) {
   using Cfg = ovg::Gemm2Cfg<BN>;
   static bool attr_set = false;
@@ -181,7 +180,7 @@ int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap
   const int tiles = ((p.M + 255) / 256) * ((p.N + BN - 1) / BN);
   const int pairs = num_sms() / 2;
   const int grid = 2 * (tiles < pairs ? tiles : pairs);
-  kern<<<grid, ovg::GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, to, p);
+  kern<<<grid, ovg::GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, to[0], to[1], to[2], p);
   return post_launch("ovg_gemm(2sm)");
 }
 
@@ -327,13 +326,22 @@ int ovg_gemm(const ovg_gemm_args* a, void* stream) {
     rc = get_map(a->b, ktot, a->n, 0, a->ldb, pbn / 2, &tb);
     if (rc) return rc;
     // staged epilogue (smem -> TMA store / fp32 reduce-add) whenever output rows are the GEMM rows
-    CUtensorMap to = ta;
+    CUtensorMap to[3] = {ta, ta, ta};
     const bool stage_ok = g_stage_default &&
                           ((a->epi == OVG_EPI_RESID && !a->row_index) ||
                            (a->epi == OVG_EPI_BF16 && (a->rowmap == OVG_ROWS_IDENT || a->rowmap == OVG_ROWS_PAD)));
     if (stage_ok) {
-      rc = get_out_map(a->out, a->epi == OVG_EPI_RESID, a->n, a->m, a->ldo, &to);
+      rc = get_out_map(a->out, a->epi == OVG_EPI_RESID, a->n, a->m, a->ldo, &to[0]);
       if (rc) return rc;
+      p.staged = 1;
+    } else if (g_stage_default && a->epi == OVG_EPI_QKV) {
+      // head-major q / k / v [batch * heads, ntok, 64]: one 32-token x 64 box per bulk store
+      const unsigned long long bh = static_cast<unsigned long long>(a->m / a->ntok) * (a->C / 64);
+      const void* outs[3] = {a->q_out, a->k_out, a->v_out};
+      for (int i = 0; i < 3; ++i) {
+        rc = get_map(outs[i], 64, a->ntok, bh, 64, 32, &to[i]);
+        if (rc) return rc;
+      }
       p.staged = 1;
     }
     if (pbn == 256) {
@@ -377,16 +385,22 @@ int ovg_attention(const void* q, const void* k, const void* v, void* out, int ba
   if (rc) return rc;
   static bool attr_set = false;
   if (!attr_set) {
-    OVG_CUDA(cudaFuncSetAttribute(ovg::attn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ovg::ATT_SMEM_BYTES));
-    OVG_CUDA(cudaFuncSetAttribute(ovg::attn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ovg::ATT_SMEM_BYTES));
+    OVG_CUDA(cudaFuncSetAttribute(ovg::attn2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ovg::ATT_SMEM_BYTES));
+    OVG_CUDA(cudaFuncSetAttribute(ovg::attn1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ovg::ATT1_SMEM_BYTES));
+    OVG_CUDA(cudaFuncSetAttribute(ovg::attn1_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     attr_set = true;
   }
   ovg::AttnParams p{n, heads, heads * 64, reinterpret_cast<__nv_bfloat16*>(out), g_attn_prof};
-  dim3 grid((n + 255) / 256, heads, batch);
-  if (g_attn_half)
-    ovg::attn_kernel<true><<<grid, ovg::ATT_THREADS_HALF, ovg::ATT_SMEM_BYTES, st>>>(tq, tk, tv, p);
-  else
-    ovg::attn_kernel<false><<<grid, ovg::ATT_THREADS, ovg::ATT_SMEM_BYTES, st>>>(tq, tk, tv, p);
+  // default: single-tile kernel, two CTAs per SM (measured 655 vs 678 us on the global attention of cfg2);
+  // OVG_ATTN_SINGLE=0 selects the paired kernel (256 query rows per CTA) for A/B runs
+  static const int attn_single = [] { const char* e = getenv("OVG_ATTN_SINGLE"); return e ? atoi(e) : 1; }();
+  if (attn_single) {
+    dim3 grid1((n + 127) / 128, heads, batch);
+    ovg::attn1_kernel<<<grid1, ovg::ATT1_THREADS, ovg::ATT1_SMEM_BYTES, st>>>(tq, tk, tv, p);
+  } else {
+    dim3 grid((n + 255) / 256, heads, batch);
+    ovg::attn2_kernel<<<grid, ovg::ATT_THREADS, ovg::ATT_SMEM_BYTES, st>>>(tq, tk, tv, p);
+  }
   return post_launch("ovg_attention");
 }
 

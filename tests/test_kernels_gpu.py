@@ -99,8 +99,13 @@ def test_gemm_qkv_epilogue(C, frames, hp, wp, S, bn):
         if M % ntok:
             continue
         nb = M // ntok
-        q = torch.zeros(nb, heads, ntok, 64, device="cuda", dtype=BF16)
-        k, v = torch.zeros_like(q), torch.zeros_like(q)
+        # outputs carved out of sentinel-filled buffers: bulk stores that straddle a sequence boundary must not touch
+        # anything outside [nb, heads, ntok, 64]
+        guard = 4096
+        bufs = [torch.full((guard + nb * heads * ntok * 64 + guard,), 7.0, device="cuda", dtype=BF16) for _ in range(3)]
+        q, k, v = (b[guard:-guard].view(nb, heads, ntok, 64) for b in bufs)
+        for t in (q, k, v):
+            t.zero_()
         ops.qkv_proj(a, w, bias, qn_w, qn_b, kn_w, kn_b, q, k, v, ntok=ntok, T=T, nspecial=5, wp=wp, rope_cos=cos, rope_sin=sin, block_n=bn)
         qkv = (a.float() @ w.float().t() + bias).reshape(nb, ntok, 3, heads, 64).permute(2, 0, 3, 1, 4)
         yy, xx = torch.meshgrid(torch.arange(hp, device="cuda"), torch.arange(wp, device="cuda"), indexing="ij")
@@ -110,6 +115,8 @@ def test_gemm_qkv_epilogue(C, frames, hp, wp, S, bn):
         kr = _rope_ref(F.layer_norm(qkv[1], (64,), kn_w, kn_b, 1e-5), pos)
         torch.cuda.synchronize()
         assert rel(q, qr) < 6e-3 and rel(k, kr) < 6e-3 and rel(v, qkv[2]) < 6e-3
+        for b in bufs:
+            assert (b[:guard] == 7.0).all() and (b[-guard:] == 7.0).all()
 
 
 # ----------------------------------------------------------------------------------------------- attention
