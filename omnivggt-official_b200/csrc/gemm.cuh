@@ -38,6 +38,7 @@ struct GemmParams {
   // ---- EPI_RESID:  out(fp32)[row,n] += gamma[n] * (acc + bias[n]),  row = row_index ? row_index[m] : m
   const float* gamma;
   const int* row_index;
+  int split_tail;  // pair kernel, BN = 256: the tiles of the last (partial) wave are issued as two 256 x 128 halves
   int staged;  // 1: epilogue output goes through smem + TMA (store for EPI_BF16, fp32 reduce-add for EPI_RESID)
   // ---- EPI_QKV (layers/attention.py:52-58 fused: bias, q/k LayerNorm(64), 2-D RoPE, head-major bf16)
   __nv_bfloat16* q_out;
@@ -621,8 +622,8 @@ struct Gemm2Cfg {
 template <int BN, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-             const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmO2,
-             const __grid_constant__ CUtensorMap tmO3, const GemmParams p) {
+             const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmO,
+             const __grid_constant__ CUtensorMap tmO2, const __grid_constant__ CUtensorMap tmO3, const GemmParams p) {
   using Cfg2 = Gemm2Cfg<BN>;
   constexpr int STAGES = Cfg2::STAGES;
   constexpr int GEMM2_B_BYTES = Cfg2::B_BYTES;
@@ -649,10 +650,21 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   const int m_tiles = (p.M + 255) / 256;
   const int n_tiles = (p.N + BN - 1) / BN;
   const int num_tiles = m_tiles * n_tiles;
+  // Wave quantisation: with T tiles on G clusters the last wave holds T mod G tiles and the other clusters idle for a
+  // whole tile time (proj / fc2 at cfg2: 172 tiles on 74 clusters = 2.32 waves, paid as 3).  When that remainder fits
+  // twice into the machine its tiles are issued as two 256 x 128 halves (tmBh: 64 B rows per CTA, N = 128 MMAs, the
+  // BN = 128 epilogue), so the tail costs half a tile time.  All three roles walk the same sequence `it`.
+  const int full_tiles = (BN == 256 && p.split_tail) ? (num_tiles / num_clusters) * num_clusters : num_tiles;
+  const int num_items = full_tiles + 2 * (num_tiles - full_tiles);
+#define OVG_GEMM2_ITEM(it)                                                          \
+  const bool half_tile = (it) >= full_tiles;                                        \
+  const int tile = half_tile ? full_tiles + (((it) - full_tiles) >> 1) : (it);      \
+  const int hsel = half_tile ? (((it) - full_tiles) & 1) : 0;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (BN == 256 && p.split_tail) tma_prefetch_desc(&tmBh);
     if (p.staged) {
       tma_prefetch_desc(&tmO);
       if (EPI == EPI_QKV) {
@@ -699,20 +711,23 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      for (int it = cluster_id; it < num_items; it += num_clusters) {
+        OVG_GEMM2_ITEM(it)
         const int m0 = (tile / n_tiles) * 256 + static_cast<int>(rank) * 128;
-        const int n0 = (tile % n_tiles) * BN + static_cast<int>(rank) * (BN / 2);
+        const int n0 = half_tile ? (tile % n_tiles) * BN + hsel * (BN / 2) + static_cast<int>(rank) * (BN / 4)
+                                 : (tile % n_tiles) * BN + static_cast<int>(rank) * (BN / 2);
+        const uint32_t stage_tx = half_tile ? GEMM_A_BYTES + GEMM2_B_BYTES / 2 : GEMM2_STAGE_BYTES;
         for (int kb = 0; kb < p.k_blocks; ++kb) {
           mbar_wait(&empty[s], ph ^ 1);
           const uint32_t lead_full = mapa_u32(smem_u32(&full[s]), 0);
           // Only the leader arrives; the peer's TMA bytes are accounted for by the leader's expect_tx (the transaction
           // count may go transiently negative, which mbarrier allows).  The peer cannot run a phase ahead: it refills
           // stage s only after the MMA that consumed the previous fill has committed to its empty[s].
-          if (leader) mbar_expect_tx(&full[s], 2 * GEMM2_STAGE_BYTES);
+          if (leader) mbar_expect_tx(&full[s], 2 * stage_tx);
           const int tap = kb / p.kc_blocks;
           const int c0 = (kb - tap * p.kc_blocks) * GEMM_BK;
           tma_load_2d_2sm(sA + s * GEMM_A_BYTES, &tmA, lead_full, c0, m0 + p.tap_off[tap]);
-          tma_load_2d_2sm(sB + s * GEMM2_B_BYTES, &tmB, lead_full, kb * GEMM_BK, n0);
+          tma_load_2d_2sm(sB + s * GEMM2_B_BYTES, half_tile ? &tmBh : &tmB, lead_full, kb * GEMM_BK, n0);
           if (++s == STAGES) {
             s = 0;
             ph ^= 1;
@@ -723,12 +738,14 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   } else if (warp == 1) {
     // ===================== MMA issuer (pair leader only) =====================
     if (leader && lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(256, BN, 0, 0);
+      constexpr uint32_t idesc_full = make_idesc_bf16(256, BN, 0, 0);
+      constexpr uint32_t idesc_half = make_idesc_bf16(256, BN / 2, 0, 0);
       int s = 0;
       uint32_t ph = 0;
       int as = 0;
       uint32_t aph = 0;
-      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      for (int it = cluster_id; it < num_items; it += num_clusters) {
+        const uint32_t idesc = it >= full_tiles ? idesc_half : idesc_full;
         mbar_wait(&tempty[as], aph ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BN;
@@ -760,13 +777,17 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     const int r = quarter * 32 + lane;
     int as = 0;
     uint32_t aph = 0;
-    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+    for (int it = cluster_id; it < num_items; it += num_clusters) {
+      OVG_GEMM2_ITEM(it)
       const int m = (tile / n_tiles) * 256 + static_cast<int>(rank) * 128 + r;
-      const int n0 = (tile % n_tiles) * BN;
+      const int n0 = (tile % n_tiles) * BN + hsel * (BN / 2);
       mbar_wait(&tfull[as], aph);
       tc_fence_after();
       const uint32_t trow = tmem_base + as * BN + (static_cast<uint32_t>(quarter * 32) << 16);
-      epilogue_tile<BN, EPI>(p, trow, m, n0, colhalf, s_rope, s_stage + (warp - 2) * 4096, &tmO, &tmO2, &tmO3);
+      if (half_tile)
+        epilogue_tile<BN / 2, EPI>(p, trow, m, n0, colhalf, s_rope, s_stage + (warp - 2) * 4096, &tmO, &tmO2, &tmO3);
+      else
+        epilogue_tile<BN, EPI>(p, trow, m, n0, colhalf, s_rope, s_stage + (warp - 2) * 4096, &tmO, &tmO2, &tmO3);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -779,6 +800,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       }
     }
   }
+#undef OVG_GEMM2_ITEM
   if (p.staged && warp >= 2 && lane == 0) tma_store_wait_all();   // bulk stores issued by this thread have completed
   tc_fence_before();
   cluster_sync();   // the peer may still signal barriers / read smem of this CTA until both are done

@@ -17,6 +17,7 @@ namespace {
 thread_local std::string g_err;
 std::atomic<long long> g_launches{0};
 const bool g_stage_default = [] { const char* e = getenv("OVG_GEMM_STAGE"); return !(e && e[0] == '0'); }();   // A/B switch
+const bool g_split_default = [] { const char* e = getenv("OVG_GEMM_SPLIT"); return !(e && e[0] == '0'); }();   // A/B switch
 const bool g_pair_default = [] { const char* e = getenv("OVG_GEMM_PAIR"); return !(e && e[0] == '0'); }();   // A/B switch
 
 int fail(int code, const std::string& msg) {
@@ -168,8 +169,8 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const ovg::GemmPar
 }
 
 template <int BN, int EPI>
-int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap (&to)[3], const ovg::GemmParams& p,
-                 cudaStream_t st) {
+int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tbh, const CUtensorMap (&to)[3],
+                 ovg::GemmParams& p, cudaStream_t st) {
   using Cfg = ovg::Gemm2Cfg<BN>;
   static bool attr_set = false;
   auto kern = ovg::gemm2_kernel<BN, EPI>;
@@ -180,7 +181,10 @@ int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap
   const int tiles = ((p.M + 255) / 256) * ((p.N + BN - 1) / BN);
   const int pairs = num_sms() / 2;
   const int grid = 2 * (tiles < pairs ? tiles : pairs);
-  kern<<<grid, ovg::GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, to[0], to[1], to[2], p);
+  // last partial wave as half tiles when both halves of every leftover tile find a free cluster (gemm.cuh)
+  const int tail = tiles > pairs ? tiles % pairs : 0;
+  p.split_tail = (BN == 256 && g_split_default && tail > 0 && 2 * tail <= pairs) ? 1 : 0;
+  kern<<<grid, ovg::GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, tbh, to[0], to[1], to[2], p);
   return post_launch("ovg_gemm(2sm)");
 }
 
@@ -325,6 +329,9 @@ int ovg_gemm(const ovg_gemm_args* a, void* stream) {
     const int pbn = (a->block_n == 384 || (a->block_n == 0 && a->n < 256)) ? 128 : 256;
     rc = get_map(a->b, ktot, a->n, 0, a->ldb, pbn / 2, &tb);
     if (rc) return rc;
+    CUtensorMap tbh;
+    rc = get_map(a->b, ktot, a->n, 0, a->ldb, pbn / 4, &tbh);     // half tiles of the last wave: N/4 rows of B per CTA
+    if (rc) return rc;
     // staged epilogue (smem -> TMA store / fp32 reduce-add) whenever output rows are the GEMM rows
     CUtensorMap to[3] = {ta, ta, ta};
     const bool stage_ok = g_stage_default &&
@@ -346,16 +353,16 @@ int ovg_gemm(const ovg_gemm_args* a, void* stream) {
     }
     if (pbn == 256) {
       switch (a->epi) {
-        case OVG_EPI_BF16: return launch_gemm2<256, ovg::EPI_BF16>(ta, tb, to, p, st);
-        case OVG_EPI_RESID: return launch_gemm2<256, ovg::EPI_RESID>(ta, tb, to, p, st);
-        case OVG_EPI_QKV: return launch_gemm2<256, ovg::EPI_QKV>(ta, tb, to, p, st);
+        case OVG_EPI_BF16: return launch_gemm2<256, ovg::EPI_BF16>(ta, tb, tbh, to, p, st);
+        case OVG_EPI_RESID: return launch_gemm2<256, ovg::EPI_RESID>(ta, tb, tbh, to, p, st);
+        case OVG_EPI_QKV: return launch_gemm2<256, ovg::EPI_QKV>(ta, tb, tbh, to, p, st);
         default: return fail(OVG_E_INVALID, "ovg_gemm: unknown epilogue");
       }
     }
     switch (a->epi) {
-      case OVG_EPI_BF16: return launch_gemm2<128, ovg::EPI_BF16>(ta, tb, to, p, st);
-      case OVG_EPI_RESID: return launch_gemm2<128, ovg::EPI_RESID>(ta, tb, to, p, st);
-      case OVG_EPI_QKV: return launch_gemm2<128, ovg::EPI_QKV>(ta, tb, to, p, st);
+      case OVG_EPI_BF16: return launch_gemm2<128, ovg::EPI_BF16>(ta, tb, tbh, to, p, st);
+      case OVG_EPI_RESID: return launch_gemm2<128, ovg::EPI_RESID>(ta, tb, tbh, to, p, st);
+      case OVG_EPI_QKV: return launch_gemm2<128, ovg::EPI_QKV>(ta, tb, tbh, to, p, st);
       default: return fail(OVG_E_INVALID, "ovg_gemm: unknown epilogue");
     }
   }

@@ -32,6 +32,8 @@ def randn(*s, scale=1.0, seed=0, dtype=F32):
                                       # block_n = 512 selects the CTA-pair (cta_group::2) kernel, 256 x 256 tiles
                                       (2748, 3072, 1024, 512), (515, 1024, 4096, 512), (300, 256, 128, 512), (129, 512, 64, 512),
                                       (10992, 1024, 1024, 512),
+                                      # > 74 tiles with a short last wave: its tiles run as two 256 x 128 halves
+                                      (5000, 1024, 128, 512), (4000, 1280, 64, 512), (19000, 256, 64, 512),
                                       # block_n = 384: CTA-pair kernel with 256 x 128 tiles
                                       (2748, 384, 192, 384), (1500, 128, 2048, 384), (300, 256, 128, 384)])
 def test_gemm_bf16_bias_gelu(M, N, K, bn):
@@ -45,6 +47,20 @@ def test_gemm_bf16_bias_gelu(M, N, K, bn):
     assert rel(out, ref) < 6e-3          # bf16 output rounding ~ 2^-9
     out2 = ops.linear_bf16(a, w, None, act=ops.L.ACT_NONE, block_n=bn)
     assert rel(out2, a.float() @ w.float().t()) < 6e-3
+
+
+@pytest.mark.parametrize("M,N,K", [(5000, 1024, 128), (10992, 1024, 256)])
+def test_gemm_resid_split_tail(M, N, K):
+    """Residual epilogue (bulk reduce-add) over a tile count whose last wave is split into half tiles."""
+    ops = _ops()
+    a = randn(M, K, seed=1, dtype=BF16)
+    w = randn(N, K, scale=K ** -0.5, seed=2, dtype=BF16)
+    bias, gamma = randn(N, seed=3), randn(N, seed=4)
+    x0 = randn(M, N, seed=5)
+    x = x0.clone()
+    ops.linear_resid(a, w, bias, gamma, x, block_n=512)
+    ref = x0 + gamma * (a.float() @ w.float().t() + bias)
+    assert rel(x, ref) < 1e-5
 
 
 @pytest.mark.parametrize("bn", [0, 512])
@@ -83,7 +99,8 @@ def _rope_ref(t, pos, base=100.0):
 
 
 @pytest.mark.parametrize("C,frames,hp,wp,S,bn", [(128, 3, 4, 4, 3, 0), (1024, 2, 37, 37, 2, 0), (256, 4, 3, 5, 2, 0),
-                                                 (1024, 2, 37, 37, 2, 512), (128, 3, 4, 4, 3, 512)])
+                                                 (1024, 2, 37, 37, 2, 512), (128, 3, 4, 4, 3, 512),
+                                                 (1024, 2, 29, 30, 2, 512)])   # 84 tiles: split last wave
 def test_gemm_qkv_epilogue(C, frames, hp, wp, S, bn):
     """QKV linear + q/k LayerNorm(64) + 2-D RoPE + head-major layout vs reference formulas
     (layers/attention.py:52-58, layers/rope.py:154-188)."""
