@@ -610,6 +610,151 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 // 128 x 256 single-CTA tile needs ~87 FLOP per L2->SM byte and saturates the L2 fabric (~10-12 TB/s) near 1 PFLOP/s;
 // the paired tile needs 131 FLOP/B.  The pair leader issues M=256 MMAs that write both CTAs' TMEM; every CTA runs its own
 // TMA producer and epilogue (rows [128*rank, 128*rank+128) of the tile).
+// ---------------------------------------------------------------------------------------------------------------------
+// DPT output tail at full resolution (heads/dpt_head.py:121-126,:255-260): 3x3 conv 128 -> 32 over the zero-bordered NHWC
+// map + ReLU + 1x1 conv + activations.  With N = 32 the generic 9-tap path is bound by L2->SM traffic: it re-loads the
+// 128 x 64 A tile for every tap (18 loads of 16 KB per 128 output pixels).  Here the three horizontal taps of one kernel
+// row read ONE smem block of 136 rows through row-shifted UMMA descriptors (start address + kx * 128 B), so a tile needs 6
+// A loads instead of 18, and the 72 KB of weights are loaded once per CTA and stay resident.
+constexpr int HT_A_ROWS = 136;
+constexpr int HT_A_BYTES = HT_A_ROWS * 128;          // 17 408 = 17 swizzle atoms
+constexpr int HT_STAGES = 6;
+constexpr int HT_B_TILE = 32 * 128;                  // one [32 x 64] bf16 weight tile
+constexpr int HT_B_BYTES = 18 * HT_B_TILE;           // 9 taps x 2 K blocks
+constexpr int HT_SMEM_BYTES = HT_STAGES * HT_A_BYTES + HT_B_BYTES + 1024 + 256;
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+headtail_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p,
+                const int use_base_offset) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + HT_STAGES * HT_A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + HT_B_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + HT_STAGES;
+  uint64_t* tfull = bars + 2 * HT_STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint64_t* bfull = tempty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bfull + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = (p.M + GEMM_BM - 1) / GEMM_BM;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int i = 0; i < HT_STAGES; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 8);
+    }
+    mbar_init(bfull, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 64);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(bfull, HT_B_BYTES);
+      for (int t = 0; t < 18; ++t) tma_load_2d(sB + t * HT_B_TILE, &tmB, bfull, t * GEMM_BK, 0);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = tile * GEMM_BM;
+        for (int ky = 0; ky < 3; ++ky) {
+          const int row0 = m0 + p.tap_off[ky * 3 + 1] - 1;     // first row the kx = 0 tap reads
+          for (int kb = 0; kb < 2; ++kb) {
+            mbar_wait(&empty[s], ph ^ 1);
+            mbar_expect_tx(&full[s], HT_A_BYTES);
+            tma_load_2d(sA + s * HT_A_BYTES, &tmA, &full[s], kb * GEMM_BK, row0);
+            if (++s == HT_STAGES) {
+              s = 0;
+              ph ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(GEMM_BM, 32, 0, 0);
+      int s = 0;
+      uint32_t ph = 0;
+      int as = 0;
+      uint32_t aph = 0;
+      mbar_wait(bfull, 0);
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty[as], aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * 32;
+        for (int ky = 0; ky < 3; ++ky) {
+          for (int kb = 0; kb < 2; ++kb) {
+            mbar_wait(&full[s], ph);
+            tc_fence_after();
+            const uint32_t a_atom = smem_u32(sA + s * HT_A_BYTES);
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+              const uint64_t adesc = make_sw128_desc_rows(a_atom, kx, use_base_offset);
+              const uint64_t bdesc = make_sw128_desc(smem_u32(sB + ((ky * 3 + kx) * 2 + kb) * HT_B_TILE));
+#pragma unroll
+              for (int k = 0; k < GEMM_BK / 16; ++k)
+                umma_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (ky | kb | kx | k) != 0 ? 1u : 0u);
+            }
+            umma_commit(&empty[s]);
+            if (++s == HT_STAGES) {
+              s = 0;
+              ph ^= 1;
+            }
+          }
+        }
+        umma_commit(&tfull[as]);
+        if (++as == 2) {
+          as = 0;
+          aph ^= 1;
+        }
+      }
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int colhalf = (warp - 2) >> 2;
+    const int r = quarter * 32 + lane;
+    int as = 0;
+    uint32_t aph = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m = tile * GEMM_BM + r;
+      mbar_wait(&tfull[as], aph);
+      tc_fence_after();
+      const uint32_t trow = tmem_base + as * 32 + (static_cast<uint32_t>(quarter * 32) << 16);
+      epilogue_tile<32, EPI_HEADTAIL>(p, trow, m, 0, colhalf, nullptr);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[as]);
+      if (++as == 2) {
+        as = 0;
+        aph ^= 1;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 64);
+  }
+}
+
 constexpr int GEMM2_STG_BYTES = 8 * 4096;   // one 32 x 32 fp32 (or bf16) staging tile per epilogue warp; followed by the QKV tables
 template <int BN>
 struct Gemm2Cfg {

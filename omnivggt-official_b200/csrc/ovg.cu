@@ -373,7 +373,28 @@ int ovg_gemm(const ovg_gemm_args* a, void* stream) {
     case OVG_EPI_BF16: return dispatch_bn<ovg::EPI_BF16>(bn, ta, tb, p, st);
     case OVG_EPI_RESID: return dispatch_bn<ovg::EPI_RESID>(bn, ta, tb, p, st);
     case OVG_EPI_QKV: return dispatch_bn<ovg::EPI_QKV>(bn, ta, tb, p, st);
-    case OVG_EPI_HEADTAIL: return launch_gemm<32, ovg::EPI_HEADTAIL>(ta, tb, p, st);
+    case OVG_EPI_HEADTAIL: {
+      // row-shift kernel: 3x3 taps in row-major order over a 128-channel map ((ky, kx) -> tap_off = (ky-1)*pitch + kx-1)
+      static const int ht_mode = [] { const char* e = getenv("OVG_HT_ROWSHIFT"); return e ? atoi(e) : 1; }();   // 0: generic 9-tap path; 1: row-shifted descriptors; 2: + base-offset field (wrong on sm_100, kept for the record)
+      bool shape_ok = ht_mode > 0 && a->num_taps == 9 && a->a_cols == 128 && a->n == 32;
+      for (int ky = 0; ky < 3 && shape_ok; ++ky)
+        shape_ok = a->tap_off[ky * 3 + 1] - a->tap_off[ky * 3] == 1 && a->tap_off[ky * 3 + 2] - a->tap_off[ky * 3 + 1] == 1;
+      if (!shape_ok) return launch_gemm<32, ovg::EPI_HEADTAIL>(ta, tb, p, st);
+      CUtensorMap ta136, tb32;
+      rc = get_map(a->a, a->a_cols, a->a_rows, 0, a->lda, ovg::HT_A_ROWS, &ta136);
+      if (rc) return rc;
+      rc = get_map(a->b, ktot, a->n, 0, a->ldb, 32, &tb32);
+      if (rc) return rc;
+      static bool attr_set = false;
+      if (!attr_set) {
+        OVG_CUDA(cudaFuncSetAttribute(ovg::headtail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ovg::HT_SMEM_BYTES));
+        attr_set = true;
+      }
+      const int tiles = (p.M + ovg::GEMM_BM - 1) / ovg::GEMM_BM;
+      const int grid = tiles < num_sms() ? tiles : num_sms();
+      ovg::headtail_kernel<<<grid, ovg::GEMM_THREADS, ovg::HT_SMEM_BYTES, st>>>(ta136, tb32, p, ht_mode == 2 ? 1 : 0);
+      return post_launch("ovg_gemm(headtail)");
+    }
     default: return fail(OVG_E_INVALID, "ovg_gemm: unknown epilogue");
   }
 }
