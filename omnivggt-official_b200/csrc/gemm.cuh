@@ -651,7 +651,7 @@ headtail_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 8);
+      mbar_init(&tempty[i], 4);
     }
     mbar_init(bfull, 1);
     fence_barrier_init();
@@ -727,24 +727,25 @@ headtail_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
     }
   } else {
+    // The tile is only 32 columns wide, so a column split would leave half of the epilogue warps idle; instead the two
+    // warp sets (2-5, 6-9) own one accumulator stage each and take alternate tiles (the per-row 1x1 conv + activations
+    // + strided fp32 stores are latency-bound).
     const int quarter = warp & 3;
-    const int colhalf = (warp - 2) >> 2;
+    const int eset = (warp - 2) >> 2;          // == accumulator stage this warp set serves
     const int r = quarter * 32 + lane;
-    int as = 0;
     uint32_t aph = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    int seq = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++seq) {
+      if ((seq & 1) != eset) continue;
       const int m = tile * GEMM_BM + r;
-      mbar_wait(&tfull[as], aph);
+      mbar_wait(&tfull[eset], aph);
       tc_fence_after();
-      const uint32_t trow = tmem_base + as * 32 + (static_cast<uint32_t>(quarter * 32) << 16);
-      epilogue_tile<32, EPI_HEADTAIL>(p, trow, m, 0, colhalf, nullptr);
+      const uint32_t trow = tmem_base + eset * 32 + (static_cast<uint32_t>(quarter * 32) << 16);
+      epilogue_tile<32, EPI_HEADTAIL>(p, trow, m, 0, 0, nullptr);
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[as]);
-      if (++as == 2) {
-        as = 0;
-        aph ^= 1;
-      }
+      if (lane == 0) mbar_arrive(&tempty[eset]);
+      aph ^= 1;
     }
   }
   tc_fence_before();

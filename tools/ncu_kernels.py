@@ -1,5 +1,6 @@
 """The block-level kernels at cfg2 shapes, one launch each inside a cudaProfiler range (for `ncu --set full`):
    0 qkv fused (LN + RoPE epilogue)   1 proj (residual)   2 fc1 (GELU)   3 fc2 (residual)   4 global attention   5 layernorm
+   6 DPT tail (3x3 conv 128->32 + 1x1 + activations, 8 frames @ 518^2)   7 bilinear upsampling 296^2 -> 518^2 (128 ch)
 """
 import os
 import sys
@@ -38,6 +39,20 @@ ln_w, ln_b = torch.ones(C, device=dev), torch.zeros(C, device=dev)
 ln_out = torch.empty(M, C, device=dev, dtype=BF16)
 
 
+Fr, hh, ww = 8, 518, 518
+xt = torch.zeros(Fr, hh + 2, ww + 2, 128, device=dev, dtype=BF16)
+xt[:, 1:-1, 1:-1] = torch.randn(Fr, hh, ww, 128, device=dev, generator=g).to(BF16)
+wt = (rn(32, 9 * 128) * (9 * 128) ** -0.5).to(BF16)
+bt, w2t, b2t = rn(32) * 0.1, (rn(4, 32) * 32 ** -0.5).contiguous(), rn(4) * 0.1
+preds = torch.zeros(Fr, hh, ww, 3, device=dev)
+conf = torch.zeros(Fr, hh, ww, device=dev)
+taps = [(ky - 1) * (ww + 2) + (kx - 1) for ky in range(3) for kx in range(3)]
+xs = torch.zeros(Fr, 298, 298, 128, device=dev, dtype=BF16)
+xs[:, 1:-1, 1:-1] = torch.randn(Fr, 296, 296, 128, device=dev, generator=g).to(BF16)
+xu = torch.empty(Fr, hh + 2, ww + 2, 128, device=dev, dtype=BF16)
+tx, ty = rn(ww, 64), rn(hh, 64)
+
+
 def run():
     ops.qkv_proj(a, wqkv, bqkv, ones, zeros, ones, zeros, q, k, v, ntok=M, T=T, nspecial=5, wp=37, rope_cos=cos, rope_sin=sin)
     ops.linear_resid(a, wproj, bproj, gamma, x)
@@ -45,6 +60,9 @@ def run():
     ops.linear_resid(h, w2, b2, gamma, x)
     ops.attention(q, k, v, o, 1, 16, M)
     ops.layernorm(x, ln_out, ln_w, ln_b)
+    ops.gemm(xt.reshape(-1, 128), wt, taps=taps, epi=ops.L.EPI_HEADTAIL, bias=bt, w2=w2t, b2=b2t, outc=4, head_act=1,
+             preds=preds, conf=conf, rowmap=ops.L.ROWS_PAD, gh=hh, gw=ww)
+    ops.upsample_bilinear(xs, xu, tx, ty, Fr, 296, 296, hh, ww, 128)
 
 
 for _ in range(2):
