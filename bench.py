@@ -83,14 +83,13 @@ def run_reference(args, rank, world):
     GPU box).  Rank 0 only."""
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1 to its workers; this arm must use every host core it can get, so the variables
+    # are dropped BEFORE torch / MKL / OpenMP initialise (setting the thread count afterwards left MKL single-threaded:
+    # 246 s per view-set on a 128-thread box instead of ~70 s) and torch picks its default (one thread per physical core)
+    for var in ("OMP_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ.pop(var, None)
     import torch
     from oracle import cpu_baseline as cb
-    # torchrun exports OMP_NUM_THREADS=1 for multi-rank launches; this arm must use every host core it can get
-    try:
-        ncpu = len(os.sched_getaffinity(0))
-    except AttributeError:
-        ncpu = os.cpu_count() or 1
-    torch.set_num_threads(max(1, ncpu))
     for _ in range(max(args.warmup, 0) and 1):          # one warm-up sample is enough to page in MKL / weights
         cb.sample()
     secs = []
