@@ -79,25 +79,10 @@ struct GemmCfg {
 };
 
 // Exact-erf GELU (nn.GELU() default, reference layers/mlp.py:22,:36) with erf evaluated by Abramowitz-Stegun 7.1.26
-// (|abs err| <= 1.5e-7, three orders below the bf16 output resolution) on 2 MUFU + ~12 FMA-pipe instructions; erff()
-// costs ~3x more and made the fc1 epilogue longer than its K = 1024 mainloop.
-__device__ __forceinline__ float gelu_erf(float x) {
-  const float z = fabsf(x) * 0.70710678118654752f;
-  float t;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
-  float poly = fmaf(1.061405429f, t, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
-  poly *= t;
-  float e;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * z * -1.4426950408889634f));
-  const float erf_abs = fmaf(-poly, e, 1.0f);
-  return 0.5f * x * (1.0f + copysignf(erf_abs, x));
-}
-
-// Two values at a time on the packed fp32x2 pipes (FFMA2 / FMUL2): same formula, ~9 instead of ~16 issue slots per
-// element.  The epilogue warps of the fc1 GEMM are issue-bound (2 warps per SM sub-partition, 32 768 GELUs per tile).
+// (|abs err| <= 1.5e-7, three orders below the bf16 output resolution): 2 MUFU (rcp, ex2) + FMA-pipe work per element;
+// erff() costs ~3x more and made the fc1 epilogue longer than its K = 1024 mainloop.
+// Two values at a time on the packed fp32x2 pipes (FFMA2 / FMUL2): ~9 instead of ~16 issue slots per element for the
+// scalar form.  The epilogue warps of the fc1 GEMM are issue-bound (2 warps per SM sub-partition, 32 768 GELUs per tile).
 __device__ __forceinline__ float2 gelu_erf2(const float2 x) {
   const float2 z = make_float2(fabsf(x.x) * 0.70710678118654752f, fabsf(x.y) * 0.70710678118654752f);
   const float2 d = ffma2(make_float2(0.3275911f, 0.3275911f), z, make_float2(1.0f, 1.0f));

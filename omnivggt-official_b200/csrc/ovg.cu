@@ -525,6 +525,13 @@ int ovg_upsample_bilinear(const void* src, void* dst, const float* tx, const flo
                         F, h, w, H, W, C,
                         H > 1 ? static_cast<float>(h - 1) / static_cast<float>(H - 1) : 0.f,
                         W > 1 ? static_cast<float>(w - 1) / static_cast<float>(W - 1) : 0.f};
+  static const int rows_kernel = [] { const char* e = getenv("OVG_UPSAMPLE_ROWS"); return e ? atoi(e) : 1; }();   // A/B switch
+  const size_t row_smem = static_cast<size_t>(w) * 32 * sizeof(float);
+  if (rows_kernel && C % 32 == 0 && row_smem <= 48 * 1024 && C / 32 <= 65535) {
+    dim3 grid(H + 2, F, C / 32);
+    ovg::upsample_rows_kernel<<<grid, 256, row_smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    return post_launch("ovg_upsample_bilinear");
+  }
   const int per_row = (W + 2) * (C / 8);
   dim3 grid((per_row + 255) / 256, H + 2, F);
   ovg::upsample_bilinear_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
