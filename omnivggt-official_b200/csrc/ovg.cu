@@ -143,24 +143,38 @@ int get_out_map(const void* ptr, bool f32, unsigned long long cols, unsigned lon
   return OVG_OK;
 }
 
-int num_sms() {
-  static int n = [] {
-    int dev = 0, v = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
-    return v;
-  }();
-  return n;
+// Function attributes and the SM count are per device: one process may drive several GPUs (or several host threads).
+constexpr int kMaxDevices = 64;
+int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return dev >= 0 && dev < kMaxDevices ? dev : 0;
 }
+int num_sms() {
+  static std::atomic<int> n[kMaxDevices];
+  const int dev = current_device();
+  int v = n[dev].load(std::memory_order_relaxed);
+  if (v == 0) {
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    n[dev].store(v, std::memory_order_relaxed);
+  }
+  return v;
+}
+// true exactly until `mark_done` has been called for (slot, current device); setting an attribute twice is harmless
+struct PerDeviceOnce {
+  std::atomic<bool> done[kMaxDevices];
+  bool needed() { return !done[current_device()].load(std::memory_order_acquire); }
+  void mark_done() { done[current_device()].store(true, std::memory_order_release); }
+};
 
 template <int BN, int EPI>
 int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const ovg::GemmParams& p, cudaStream_t st) {
   using Cfg = ovg::GemmCfg<BN>;
-  static bool attr_set = false;
+  static PerDeviceOnce once;
   auto kern = ovg::gemm_kernel<BN, EPI>;
-  if (!attr_set) {
+  if (once.needed()) {
     OVG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_set = true;
+    once.mark_done();
   }
   const int tiles = ((p.M + 127) / 128) * ((p.N + BN - 1) / BN);
   const int grid = tiles < num_sms() ? tiles : num_sms();
@@ -172,11 +186,11 @@ template <int BN, int EPI>
 int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tbh, const CUtensorMap (&to)[3],
                  ovg::GemmParams& p, cudaStream_t st) {
   using Cfg = ovg::Gemm2Cfg<BN>;
-  static bool attr_set = false;
+  static PerDeviceOnce once;
   auto kern = ovg::gemm2_kernel<BN, EPI>;
-  if (!attr_set) {
+  if (once.needed()) {
     OVG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_set = true;
+    once.mark_done();
   }
   const int tiles = ((p.M + 255) / 256) * ((p.N + BN - 1) / BN);
   const int pairs = num_sms() / 2;
@@ -385,10 +399,10 @@ int ovg_gemm(const ovg_gemm_args* a, void* stream) {
       if (rc) return rc;
       rc = get_map(a->b, ktot, a->n, 0, a->ldb, 32, &tb32);
       if (rc) return rc;
-      static bool attr_set = false;
-      if (!attr_set) {
+      static PerDeviceOnce once;
+      if (once.needed()) {
         OVG_CUDA(cudaFuncSetAttribute(ovg::headtail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ovg::HT_SMEM_BYTES));
-        attr_set = true;
+        once.mark_done();
       }
       const int tiles = (p.M + ovg::GEMM_BM - 1) / ovg::GEMM_BM;
       const int grid = tiles < num_sms() ? tiles : num_sms();
@@ -405,29 +419,29 @@ int ovg_attention(const void* q, const void* k, const void* v, void* out, int ba
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   CUtensorMap tq, tk, tv;
   const unsigned long long bh = static_cast<unsigned long long>(batch) * heads;
+  static const int attn_kernel = [] { const char* e = getenv("OVG_ATTN_KERNEL"); return e ? atoi(e) : 3; }();   // A/B run only
+  const unsigned kv_box = attn_kernel == 1 ? 128 : 64;
   int rc = get_map(q, 64, n, bh, 64, 128, &tq);
   if (rc) return rc;
-  rc = get_map(k, 64, n, bh, 64, 128, &tk);
+  rc = get_map(k, 64, n, bh, 64, kv_box, &tk);
   if (rc) return rc;
-  rc = get_map(v, 64, n, bh, 64, 128, &tv);
+  rc = get_map(v, 64, n, bh, 64, kv_box, &tv);
   if (rc) return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
-    OVG_CUDA(cudaFuncSetAttribute(ovg::attn2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ovg::ATT_SMEM_BYTES));
+  static PerDeviceOnce once;
+  if (once.needed()) {
     OVG_CUDA(cudaFuncSetAttribute(ovg::attn1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ovg::ATT1_SMEM_BYTES));
     OVG_CUDA(cudaFuncSetAttribute(ovg::attn1_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    attr_set = true;
+    OVG_CUDA(cudaFuncSetAttribute(ovg::attn3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ovg::ATT3_SMEM_BYTES));
+    OVG_CUDA(cudaFuncSetAttribute(ovg::attn3_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    once.mark_done();
   }
   ovg::AttnParams p{n, heads, heads * 64, reinterpret_cast<__nv_bfloat16*>(out), g_attn_prof};
-  // default: single-tile kernel, two CTAs per SM (measured 655 vs 678 us on the global attention of cfg2);
-  // OVG_ATTN_SINGLE=0 selects the paired kernel (256 query rows per CTA) for A/B runs
-  static const int attn_single = [] { const char* e = getenv("OVG_ATTN_SINGLE"); return e ? atoi(e) : 1; }();
-  if (attn_single) {
+  if (attn_kernel == 1) {
     dim3 grid1((n + 127) / 128, heads, batch);
     ovg::attn1_kernel<<<grid1, ovg::ATT1_THREADS, ovg::ATT1_SMEM_BYTES, st>>>(tq, tk, tv, p);
   } else {
     dim3 grid((n + 255) / 256, heads, batch);
-    ovg::attn2_kernel<<<grid, ovg::ATT_THREADS, ovg::ATT_SMEM_BYTES, st>>>(tq, tk, tv, p);
+    ovg::attn3_kernel<<<grid, ovg::ATT3_THREADS, ovg::ATT3_SMEM_BYTES, st>>>(tq, tk, tv, p);
   }
   return post_launch("ovg_attention");
 }

@@ -122,6 +122,8 @@ class Engine:
         self.R = ag.register_token.shape[2]
         self.depth = len(ag.frame_blocks)
         self.heads = self.C // 64
+        if self.C % 64:
+            raise ValueError(f"embed_dim {self.C}: the attention / QKV kernels are built for head_dim 64 (embed_dim % 64 == 0)")
         self.patch = model.patch_size
         self.frame = [pack_block(b) for b in ag.frame_blocks]
         self.glob = [pack_block(b) for b in ag.global_blocks]
@@ -138,6 +140,9 @@ class Engine:
         self.dino = None
         pe = ag.patch_embed
         if hasattr(pe, "blocks") and getattr(model, "dino_backend", "ovg") == "ovg":
+            if self.C // pe.heads != 64:
+                raise ValueError(f"DINOv2 patchifier with head_dim {self.C // pe.heads}: libovg attention needs head_dim 64 "
+                                 "(use dino_backend='torch' for other widths)")
             w = pe.patch_embed.proj.weight.detach().flatten(1)                       # [C, 3*p*p]
             kpad = (w.shape[1] + 7) // 8 * 8
             wpad = torch.zeros(w.shape[0], kpad, device=self.device, dtype=BF16)
@@ -160,10 +165,9 @@ class Engine:
         return self._rope[maxpos]
 
     def cached(self, key: tuple, make) -> torch.Tensor:
+        # never evicted: captured CUDA graphs hold raw pointers to these tensors (a few KB per input signature)
         t = self._idx_cache.get(key)
         if t is None:
-            if len(self._idx_cache) > 64:
-                self._idx_cache.clear()
             t = make().to(self.device)
             self._idx_cache[key] = t
         return t
@@ -179,6 +183,15 @@ class Engine:
         if key not in self._tables:
             self._tables[key] = uv_posembed_separable(C, h, w, aspect, self.device)
         return self._tables[key]
+
+    def warm_tables(self, H: int, W: int):
+        """Build the UV position-embedding tables of this image size on the CURRENT stream (the two DPT heads run on
+        different streams and share the cached tables; the first use must not race with the copy that fills them)."""
+        hp, wp = H // self.patch, W // self.patch
+        for pk in self.dpt_packs.values():
+            for oc in pk.oc:
+                self.table(oc, hp, wp, W / H)
+            self.table_xy(pk.feat // 2, hp * self.patch, wp * self.patch, W / H)
 
     # ------------------------------------------------------------------------------------------ DINOv2 patchifier
     def dino_patchify(self, images: torch.Tensor, pos_embed: torch.Tensor, mean, std) -> torch.Tensor:
@@ -265,6 +278,8 @@ class Engine:
                 ((torch.arange(B)[:, None] * S + torch.tensor(depth_idx)[None]) * T)[:, :, None] + (R + 1) +
                 torch.arange(P)[None, None]).reshape(-1).to(torch.int32))
             ops.linear_resid(cols, self.depth_w, self.depth_b, self.ones_c, x2, row_index=rows)
+        if max(hp, wp) + 1 > 64:
+            raise ValueError(f"{H}x{W} input: the fused RoPE epilogue holds 64 positions per axis (at most 882 px per side)")
         rope = self.rope(max(hp, wp) + 1)
         slots: Dict[int, torch.Tensor] = {}
         cam_out = ws.get("cam_out", (K, 2 * C), F32)

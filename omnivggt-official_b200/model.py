@@ -48,6 +48,7 @@ class OmniVGGT(nn.Module, PyTorchModelHubMixin):
         # replay the ~1000 kernel launches of a forward from a CUDA graph once a shape has been seen twice
         self.use_cuda_graph = (os.environ.get("OVG_CUDA_GRAPH", "1") != "0") if use_cuda_graph is None else use_cuda_graph
         self._graphs = {}
+        self.max_graphs = 8                 # captured input signatures kept (least recently used one is dropped)
         self.head_streams = os.environ.get("OVG_HEAD_STREAMS", "1") != "0"   # camera / depth / point heads on 3 streams
         self._streams = None
         pe = "conv" if "conv" in patch_embed else "dino"
@@ -139,10 +140,16 @@ class OmniVGGT(nn.Module, PyTorchModelHubMixin):
         Python costs about as much host time as the GPU needs to run them).  A graph is captured the third time a
         (shape, index-list) signature is seen; inputs are copied into static buffers, outputs are cloned."""
         need_c, need_d = len(cam_idx) > 0, len(depth_idx) > 0
-        key = (tuple(images.shape), images.dtype, tuple(depth_idx), tuple(cam_idx))
-        ent = self._graphs.get(key)
+        def sig(t):
+            return None if t is None else (tuple(t.shape), t.dtype)
+        key = (sig(images), tuple(depth_idx), tuple(cam_idx), sig(extrinsics) if need_c else None,
+               sig(intrinsics) if need_c else None, sig(depth) if need_d else None, sig(mask) if need_d else None)
+        ent = self._graphs.pop(key, None)
         if ent is None:
-            ent = self._graphs[key] = {"calls": 0, "graph": None}
+            ent = {"calls": 0, "graph": None}
+            while len(self._graphs) >= self.max_graphs:     # LRU: a graph owns static inputs + a private output pool
+                self._graphs.pop(next(iter(self._graphs)))
+        self._graphs[key] = ent                             # most recently used last
         ent["calls"] += 1
         if ent["graph"] is None and (ent["calls"] < 3 or ent.get("failed")):
             return self._forward_impl(eng, images, extrinsics, intrinsics, depth, mask, depth_idx, cam_idx)
@@ -160,11 +167,14 @@ class OmniVGGT(nn.Module, PyTorchModelHubMixin):
                 with torch.cuda.graph(g):
                     out = self._forward_impl(eng, *static, depth_idx, cam_idx)
                 ent.update(graph=g, static=static, out=out, ws_version=eng.ws.version)
-            except Exception as ex:  # capture is an optimisation of the launch mechanism only: keep the eager launches
+            except torch.cuda.OutOfMemoryError as ex:
+                # the only failure that is a property of the call, not a bug: the private pool of one more graph does not fit.
+                # Everything else (a capture-illegal operation, a kernel error) propagates.
                 ent["failed"] = True
                 ent["graph"] = None
-                warnings.warn(f"OmniVGGT: CUDA graph capture failed ({ex!r}); continuing with eager kernel launches")
+                warnings.warn(f"OmniVGGT: no memory for another CUDA graph ({ex}); this signature keeps eager launches")
                 torch.cuda.synchronize()
+                torch.cuda.empty_cache()
                 return self._forward_impl(eng, images, extrinsics, intrinsics, depth, mask, depth_idx, cam_idx)
         for st, t in zip(ent["static"], dyn):
             if st is not None:
@@ -214,6 +224,7 @@ class OmniVGGT(nn.Module, PyTorchModelHubMixin):
         # (forked / joined with events, also inside a captured CUDA graph) so that their many small kernels -- 19^2 / 37^2
         # feature maps, M = 8 GEMVs -- share the 148 SMs instead of running one after the other.
         predictions: Dict[str, object] = {}
+        eng.warm_tables(H, W)
         d_out = eng.dpt_alloc("depth_head", K, H, W)
         p_out = eng.dpt_alloc("point_head", K, H, W)
         main = torch.cuda.current_stream() if images.is_cuda else None

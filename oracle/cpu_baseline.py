@@ -1,9 +1,10 @@
 """CPU baseline for bench.py  --  TEST INFRASTRUCTURE (see oracle/omnivggt_oracle.py).
 
-The reference is pure Python/PyTorch and cannot travel to the GPU box, so the CPU arm times the oracle port
-(``kind: "port"``) of the same workload (cfg2: 1 scene x 8 views @ 518 x 518, images-only, fp32, all host threads).
-A full forward costs ~95 s on 8 threads, so each sample times ONE of each repeated unit at the
-full workload shape and scales by the unit counts of the real model:
+Bounded CPU sample for the ``cpu_baseline`` field of the product bench line (``kind: "port"``): the oracle port on the
+workload's shapes (1 scene x S views @ 518 x 518, fp32, all host threads).  A full forward costs ~95 s on 8 threads
+ -- the whole-forward measurement is ``bench.py --impl reference`` (the reference itself from
+oracle/_ref); here each sample times ONE of each repeated unit at the full workload shape and scales by the unit counts
+of the real model:
     t = t_patch_embed + 24 * t_dino_block + 24 * (t_frame_block + t_global_block) + 8 * t_dpt_frame(2 heads)
         + 4/trunk * t_camera_head
 Every unit is executed at full width (C = 1024, 16 heads, L = 8 * 1374 tokens, DPT features 256) on real-shaped data."""
@@ -21,10 +22,15 @@ _CACHE: Dict[str, object] = {}
 
 
 def _schema():
-    from omnivggt_official_b200 import OmniVGGT
-    with torch.device("meta"):
-        m = OmniVGGT(depth=1, dino_depth=1, dpt_layers=(0, 0, 0, 0), camera_trunk_depth=1, init_seed=None)
-    return {k: list(v.shape) for k, v in m.state_dict().items()}
+    """Names + shapes of ONE of each repeated unit, read from the reference's own key schema (tests/golden/full.schema.json,
+    written by oracle/make_golden_full.py): block / adapter indices other than 0 are dropped."""
+    import json
+    import os
+    import re
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "full.schema.json")
+    full = json.load(open(path))["schema"]
+    rep = re.compile(r"\.(blocks|frame_blocks|global_blocks|trunk|pose_embeddings|camera_adapters)\.(\d+)\.")
+    return {k: v for k, v in full.items() if all(int(m.group(2)) == 0 for m in rep.finditer(k))}
 
 
 def _state():

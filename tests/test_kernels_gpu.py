@@ -137,7 +137,8 @@ def test_gemm_qkv_epilogue(C, frames, hp, wp, S, bn):
 
 
 # ----------------------------------------------------------------------------------------------- attention
-@pytest.mark.parametrize("batch,heads,n", [(1, 1, 128), (1, 2, 256), (2, 2, 200), (3, 2, 1374), (1, 16, 2 * 1374), (1, 4, 700)])
+@pytest.mark.parametrize("batch,heads,n", [(1, 1, 128), (1, 2, 256), (2, 2, 200), (3, 2, 1374), (1, 16, 2 * 1374), (1, 4, 700), (1, 2, 1), (2, 1, 33),
+                                           (1, 3, 64), (1, 2, 129), (1, 2, 257), (1, 2, 320), (2, 3, 385)])
 def test_attention(batch, heads, n):
     """vs softmax(q k^T / 8) v in fp32 (layers/attention.py:61-66).  bf16 P and bf16 output: rel-L2 < 1e-2."""
     ops = _ops()
@@ -153,6 +154,47 @@ def test_attention(batch, heads, n):
     torch.cuda.synchronize()
     assert torch.isfinite(out.float()).all()
     assert rel(out, ref) < 1e-2, rel(out, ref)
+
+
+def _sdpa_fp32_chunked(qs, kb, vb, qchunk=4096):
+    """softmax(q k^T) v in fp32, one head and `qchunk` query rows at a time (the score matrix of the 24-view global
+    attention is 16 x 32 976^2 fp32 = 70 GB in one piece)."""
+    batch, heads, n, _ = qs.shape
+    out = torch.empty(batch, n, heads * 64, device=qs.device, dtype=F32)
+    ln2 = math.log(2.0)
+    for b in range(batch):
+        for h in range(heads):
+            kf, vf = kb[b, h].float(), vb[b, h].float()
+            for i0 in range(0, n, qchunk):
+                s = (qs[b, h, i0:i0 + qchunk].float() * ln2) @ kf.t()
+                out[b, i0:i0 + qchunk, h * 64:(h + 1) * 64] = s.softmax(-1) @ vf
+    return out
+
+
+@pytest.mark.parametrize("heads,n", [(16, 8 * 1374), (16, 24 * 1374)])
+def test_attention_global_sizes_of_baseline_configs(heads, n):
+    """BASELINE.json configs[1] / configs[4]: the global attention of 8 views (L = 10 992, 172 KV steps) and of 24 views
+    (L = 32 976, 516 KV steps), 16 heads, against fp32 SDPA (reference layers/attention.py:61-66) -- same 1e-2 bar as the
+    small shapes; the long accumulation (fp32 O / l in TMEM, lazy rescaling) is what is under test."""
+    ops = _ops()
+    q = randn(1, heads, n, 64, seed=1)
+    k = randn(1, heads, n, 64, seed=2)
+    v = randn(1, heads, n, 64, seed=3)
+    qs = (q * (math.log2(math.e) / 8.0)).to(BF16)
+    kb, vb = k.to(BF16), v.to(BF16)
+    del q, k, v
+    out = torch.zeros(1, n, heads * 64, device="cuda", dtype=BF16)
+    ops.attention(qs, kb, vb, out, 1, heads, n)
+    ref = _sdpa_fp32_chunked(qs, kb, vb)
+    torch.cuda.synchronize()
+    assert torch.isfinite(out.float()).all()
+    e = rel(out, ref)
+    print(f"attention n={n}: rel-L2 {e:.3e}")
+    assert e < 1e-2, e
+    out2 = torch.zeros_like(out)
+    ops.attention(qs, kb, vb, out2, 1, heads, n)
+    torch.cuda.synchronize()
+    assert torch.equal(out, out2)          # run-to-run bit-identical (no atomics, no ordering races)
 
 
 def test_attention_peaky_rows_rescale():

@@ -153,6 +153,58 @@ def test_full_width_vs_oracle(aux):
         assert errs[k] < TOL, errs
 
 
+# ------------------------------------------------------------------------------------------- full-size parity pins
+FULL_INDEX = json.load(open(os.path.join(GOLDEN, "full_index.json")))
+_FULL = {}
+
+
+def full_model():
+    """The full architecture (24 + 24 blocks, DINOv2 ViT-L patchifier, 1 505 tensors) with the de-zeroed seed-0 weights the
+    reference goldens were generated with (tests/golden/full.schema.json + oracle/synth.make_state_dict)."""
+    if "m" not in _FULL:
+        from omnivggt_official_b200 import OmniVGGT
+        schema = json.load(open(os.path.join(GOLDEN, "full.schema.json")))["schema"]
+        with torch.device("cuda"):
+            m = OmniVGGT(init_seed=None)
+        sd = make_state_dict(schema, 0)
+        m.load_state_dict(sd, strict=True)       # same 1 505 keys as the reference module
+        del sd
+        _FULL["m"] = m.eval()
+    return _FULL["m"]
+
+
+@pytest.mark.parametrize("case", sorted(FULL_INDEX))
+def test_full_size_matches_reference_golden(case):
+    """BASELINE.json configs[0] ("4 views @ 518 x 518 ... value check") and aux-shaped siblings: the full model on the CUDA
+    path against outputs of the UNMODIFIED reference forward (omnivggt/models/omnivggt.py:20-68, CPU fp32; generated by
+    oracle/make_golden_full.py).  Dense outputs are compared on the stored pixel lattice (every 7th row / column)."""
+    meta = FULL_INDEX[case]
+    m = full_model()
+    st, o = meta["stride"], meta["stride"] // 2
+    inp = {k: v.cuda() for k, v in make_inputs(1, meta["S"], meta["H"], meta["W"], seed=meta["input_seed"]).items()}
+    out = m(depth_gt_index=meta["depth_gt_index"], camera_gt_index=meta["camera_gt_index"], **inp)
+    torch.cuda.synchronize()
+    ref = load_file(os.path.join(GOLDEN, f"{case}.safetensors"))
+    got = {"pose_enc": out["pose_enc"]}
+    for k in KEYS[1:]:
+        assert torch.isfinite(out[k]).all(), k
+        got[k] = out[k][:, :, o::st, o::st]
+    errs = {k: rel(got[k], ref[k]) for k in KEYS}
+    errs["pose_enc_maxabs"] = (out["pose_enc"].cpu() - ref["pose_enc"]).abs().max().item()
+    for i in range(4):
+        errs[f"pose_enc_list.{i}"] = rel(out["pose_enc_list"][i], ref[f"pose_enc_list.{i}"])
+    line = f"{case} S={meta['S']} depth_idx={meta['depth_gt_index']} cam_idx={meta['camera_gt_index']} " + json.dumps(
+        {k: round(v, 5) for k, v in errs.items()})
+    print(line)
+    d = os.path.join(os.path.dirname(GOLDEN), os.pardir, "gpurun_out")
+    if os.path.isdir(d):
+        with open(os.path.join(d, "model_parity_full.txt"), "a") as f:
+            f.write(line + "\n")
+    for k in KEYS:
+        assert got[k].shape == ref[k].shape, k
+        assert errs[k] < TOL, (k, errs)
+
+
 @pytest.mark.parametrize("S,didx,cidx", [(8, list(range(8)), list(range(8))),          # BASELINE.json configs[2]
                                          (24, [0, 3, 4, 11, 23], [0, 1, 7, 12, 20, 22])])  # configs[4]: 24 views, partial aux
 def test_full_size_configs_properties(S, didx, cidx):
