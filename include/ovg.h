@@ -122,6 +122,26 @@ int ovg_im2col3x3s2(const void* src, void* dst, int F, int h, int w, int C, void
 int ovg_upsample_bilinear(const void* src, void* dst, const float* tx, const float* ty, int F, int h, int w, int H, int W,
                           int C, void* stream);
 
+/* On-device post-processing: what inference.py does on the host right after the forward.
+ * ovg_pose_decode: pose_enc fp32 [K,9] = [t, quat xyzw, fov_h, fov_w] -> extrinsic [K,3,4] (world->camera, [R|t]),
+ * intrinsic [K,3,3] (fx = (W/2)/tan(fov_w/2), fy = (H/2)/tan(fov_h/2), principal point at the image centre; may be NULL) and
+ * cam2world [K,3,4] = closed-form SE3 inverse (may be NULL).
+ * utils/pose_enc.py:65-130, utils/rotation.py:14-44, utils/geometry.py:269-318. */
+int ovg_pose_decode(const float* pose_enc, float* extrinsic, float* intrinsic, float* cam2world, int K, int H, int W,
+                    void* stream);
+
+/* ovg_unproject_depth: world[k,v,u,:] = R_c2w ((u-cu) d/fu, (v-cv) d/fv, d) + t_c2w; depth fp32 [K,H,W], world fp32 [K,H,W,3].
+ * utils/geometry.py:151-180 (unproject_depth_map_to_point_map), :183-264; visual_util.py:42-73. */
+int ovg_unproject_depth(const float* depth, const float* intrinsic, const float* cam2world, float* world, int K, int H, int W,
+                        void* stream);
+
+/* ovg_conf_percentile_mask: threshold = numpy.percentile(conf, percent) (exact, linear interpolation),
+ * mask[i] = conf[i] >= threshold && conf[i] > floor (inference.py:132-133: floor = 0.1).  workspace: device scratch of
+ * OVG_PERCENTILE_WORKSPACE_BYTES; threshold_out: device float; count_out: device u64 (kept elements) or NULL. */
+#define OVG_PERCENTILE_WORKSPACE_BYTES (6 * 8 + 512 * 4 + 4 * 4)
+int ovg_conf_percentile_mask(const float* conf, long long n, float percent, float floor_, void* workspace,
+                             unsigned char* mask, float* threshold_out, unsigned long long* count_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

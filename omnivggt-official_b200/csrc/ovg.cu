@@ -11,6 +11,7 @@
 #include "attn.cuh"
 #include "elem.cuh"
 #include "gemm.cuh"
+#include "post.cuh"
 
 namespace {
 
@@ -550,6 +551,69 @@ int ovg_upsample_bilinear(const void* src, void* dst, const float* tx, const flo
   dim3 grid((per_row + 255) / 256, H + 2, F);
   ovg::upsample_bilinear_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
   return post_launch("ovg_upsample_bilinear");
+}
+
+int ovg_pose_decode(const float* pose_enc, float* extrinsic, float* intrinsic, float* cam2world, int K, int H, int W,
+                    void* stream) {
+  OVG_REQUIRE(pose_enc && extrinsic && K > 0 && H > 0 && W > 0, "bad arguments");
+  ovg::PoseDecodeParams p{pose_enc, extrinsic, intrinsic, cam2world, K, static_cast<float>(H), static_cast<float>(W)};
+  ovg::pose_decode_kernel<<<(K + 127) / 128, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  return post_launch("ovg_pose_decode");
+}
+
+int ovg_unproject_depth(const float* depth, const float* intrinsic, const float* cam2world, float* world, int K, int H, int W,
+                        void* stream) {
+  OVG_REQUIRE(depth && intrinsic && cam2world && world && K > 0 && H > 0 && W > 0, "bad arguments");
+  OVG_REQUIRE(K <= 65535, "too many frames");
+  OVG_REQUIRE((reinterpret_cast<uintptr_t>(depth) & 15) == 0 && (reinterpret_cast<uintptr_t>(world) & 15) == 0,
+              "depth / world must be 16-byte aligned");
+  ovg::UnprojectParams p{depth, intrinsic, cam2world, world, K, H, W};
+  const long long nq = (static_cast<long long>(H) * W + 3) / 4;
+  int bx = static_cast<int>((nq + 255) / 256);
+  const int cap = (num_sms() * 8 + K - 1) / K;       // ~8 blocks per SM over all frames, grid-stride inside
+  if (bx > cap) bx = cap > 0 ? cap : 1;
+  ovg::unproject_kernel<<<dim3(bx, K), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  return post_launch("ovg_unproject_depth");
+}
+
+int ovg_conf_percentile_mask(const float* conf, long long n, float percent, float floor_, void* workspace,
+                             unsigned char* mask, float* threshold_out, unsigned long long* count_out, void* stream) {
+  OVG_REQUIRE(conf && workspace && mask && threshold_out && n > 0, "bad arguments");
+  OVG_REQUIRE(percent >= 0.f && percent <= 100.f, "percent must be in [0, 100]");
+  OVG_REQUIRE((reinterpret_cast<uintptr_t>(conf) & 15) == 0 && (reinterpret_cast<uintptr_t>(mask) & 3) == 0 &&
+                  (reinterpret_cast<uintptr_t>(workspace) & 15) == 0,
+              "conf must be 16-byte, mask 4-byte, workspace 16-byte aligned");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  // numpy.percentile(method="linear"): virtual index p/100 * (n - 1), linear interpolation between its two neighbours
+  const double vi = static_cast<double>(percent) / 100.0 * static_cast<double>(n - 1);
+  const unsigned long long r0 = static_cast<unsigned long long>(vi);
+  const unsigned long long r1 = r0 + 1 < static_cast<unsigned long long>(n) ? r0 + 1 : r0;
+  const double frac = vi - static_cast<double>(r0);
+  // workspace: 6 x u64 state | 512 x u32 histograms | 3 x f32 results       (OVG_PERCENTILE_WORKSPACE_BYTES)
+  unsigned long long* state = reinterpret_cast<unsigned long long*>(workspace);
+  unsigned int* hist = reinterpret_cast<unsigned int*>(state + 6);
+  float* res = reinterpret_cast<float*>(hist + 512);
+  ovg::select_init_kernel<<<1, 128, 0, st>>>(state, hist, r0, r1, count_out);
+  {
+    int rc = post_launch("ovg_conf_percentile_mask(init)");
+    if (rc) return rc;
+  }
+  int blocks = static_cast<int>((n / 4 + 255) / 256);
+  if (blocks > num_sms() * 4) blocks = num_sms() * 4;
+  if (blocks < 1) blocks = 1;
+  for (int pass = 0; pass < 4; ++pass) {
+    ovg::SelectParams sp{conf, n, state, hist, pass, res, static_cast<float>(frac)};
+    ovg::select_hist_kernel<<<blocks, 256, 0, st>>>(sp);
+    int rc = post_launch("ovg_conf_percentile_mask(hist)");
+    if (rc) return rc;
+    ovg::select_decide_kernel<<<1, 32, 0, st>>>(sp);
+    rc = post_launch("ovg_conf_percentile_mask(decide)");
+    if (rc) return rc;
+  }
+  OVG_CUDA(cudaMemcpyAsync(threshold_out, res + 2, sizeof(float), cudaMemcpyDeviceToDevice, st));
+  ovg::ConfMaskParams mp{conf, res + 2, mask, n, floor_, count_out};
+  ovg::conf_mask_kernel<<<blocks, 256, 0, st>>>(mp);
+  return post_launch("ovg_conf_percentile_mask");
 }
 
 }  // extern "C"

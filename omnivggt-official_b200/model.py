@@ -134,6 +134,30 @@ class OmniVGGT(nn.Module, PyTorchModelHubMixin):
             return self._forward_graphed(eng, *args)
         return self._forward_impl(eng, *args)
 
+    # ---------------------------------------------------------------------------------------------- post-processing
+    @torch.no_grad()
+    def postprocess(self, predictions: Dict[str, object], conf_percent: float = 50.0, use_point_map: bool = False
+                    ) -> Dict[str, object]:
+        """What reference inference.py does on the host right after the forward, on the device (libovg kernels):
+        ``extrinsic`` / ``intrinsic`` from ``pose_enc`` (inference.py:360-365 -> utils/pose_enc.py:65-130),
+        ``world_points_from_depth`` by unprojecting the predicted depth with the predicted cameras (visual_util.py:42-73 ->
+        utils/geometry.py:151-264), and the confidence filter of the viewer (inference.py:132-133): ``conf_mask`` =
+        conf >= percentile(conf, conf_percent) & conf > 0.1 with ``conf_threshold`` / ``conf_kept``, over
+        ``world_points_conf`` if ``use_point_map`` else ``depth_conf`` (inference.py:95-100).  Adds the keys in place."""
+        from . import ops
+        pose = predictions["pose_enc"]
+        H, W = predictions["images"].shape[-2:]
+        B, S = pose.shape[:2]
+        ext, intr, c2w = ops.pose_decode(pose.float(), H, W)
+        predictions["extrinsic"], predictions["intrinsic"] = ext, intr
+        depth = predictions["depth"].float().reshape(B * S, H, W)
+        world = ops.unproject_depth(depth, intr.view(B * S, 3, 3), c2w.view(B * S, 3, 4), H, W)
+        predictions["world_points_from_depth"] = world.view(B, S, H, W, 3)
+        conf = predictions["world_points_conf" if use_point_map else "depth_conf"].float()
+        mask, thr, cnt = ops.conf_percentile_mask(conf, conf_percent, 0.1)
+        predictions["conf_mask"], predictions["conf_threshold"], predictions["conf_kept"] = mask.bool(), thr, cnt
+        return predictions
+
     # ---------------------------------------------------------------------------------------------- CUDA graph replay
     def _forward_graphed(self, eng, images, extrinsics, intrinsics, depth, mask, depth_idx, cam_idx):
         """Same computation, launched from a captured CUDA graph (a forward is >1000 kernel launches; issuing them from

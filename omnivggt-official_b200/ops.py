@@ -132,3 +132,40 @@ def im2col3x3s2(src, dst, F, h, w, C):
 def upsample_bilinear(src, dst, tx, ty, F, h, w, H, W, C):
     """tx [W, C/2], ty [H, C/2]: separable UV position embedding (or both None)."""
     L.check(L.lib().ovg_upsample_bilinear(src.data_ptr(), dst.data_ptr(), L.ptr(tx), L.ptr(ty), F, h, w, H, W, C, L.stream()))
+
+
+def pose_decode(pose_enc, H: int, W: int):
+    """pose_enc fp32 [..., 9] -> (extrinsic [..., 3, 4], intrinsic [..., 3, 3], cam2world [..., 3, 4]) on the device."""
+    _chk(pose_enc, F32, "pose_enc")
+    pe = pose_enc.contiguous()
+    lead = pe.shape[:-1]
+    K = pe.numel() // 9
+    ext = torch.empty(*lead, 3, 4, device=pe.device, dtype=F32)
+    intr = torch.empty(*lead, 3, 3, device=pe.device, dtype=F32)
+    c2w = torch.empty(*lead, 3, 4, device=pe.device, dtype=F32)
+    L.check(L.lib().ovg_pose_decode(pe.data_ptr(), ext.data_ptr(), intr.data_ptr(), c2w.data_ptr(), K, H, W, L.stream()))
+    return ext, intr, c2w
+
+
+def unproject_depth(depth, intrinsic, cam2world, H: int, W: int):
+    """depth fp32 [K, H, W] (contiguous) -> world points fp32 [K, H, W, 3]."""
+    _chk(depth, F32, "depth")
+    d = depth.contiguous()
+    K = d.numel() // (H * W)
+    world = torch.empty(K, H, W, 3, device=d.device, dtype=F32)
+    L.check(L.lib().ovg_unproject_depth(d.data_ptr(), intrinsic.contiguous().data_ptr(), cam2world.contiguous().data_ptr(),
+                                        world.data_ptr(), K, H, W, L.stream()))
+    return world
+
+
+def conf_percentile_mask(conf, percent: float, floor: float = 0.1):
+    """(mask uint8 like conf, threshold 0-d fp32 tensor, kept-count 0-d int64 tensor); threshold = numpy.percentile(conf, percent)."""
+    _chk(conf, F32, "conf")
+    c = conf.contiguous()
+    ws = torch.empty(L.PERCENTILE_WORKSPACE_BYTES // 8 + 1, device=c.device, dtype=torch.int64)
+    mask = torch.empty(c.shape, device=c.device, dtype=torch.uint8)
+    thr = torch.empty((), device=c.device, dtype=F32)
+    cnt = torch.empty((), device=c.device, dtype=torch.int64)
+    L.check(L.lib().ovg_conf_percentile_mask(c.data_ptr(), c.numel(), float(percent), float(floor), ws.data_ptr(),
+                                             mask.data_ptr(), thr.data_ptr(), cnt.data_ptr(), L.stream()))
+    return mask, thr, cnt
