@@ -195,7 +195,7 @@ def gpu_torch_baseline(model, inputs, cfg, dev, ours):
     with torch.device(dev):
         ref = Ref()
     ref.load_state_dict(model.state_dict(), strict=True)
-    ref.eval()
+    ref = ref.to(dev).eval()
     kw = dict(images=inputs["images"], extrinsics=inputs["extrinsics"], intrinsics=inputs["intrinsics"],
               depth=inputs["depth"], mask=inputs["mask"], depth_gt_index=list(cfg["depth_idx"]),
               camera_gt_index=list(cfg["cam_idx"]))
@@ -395,7 +395,8 @@ def main():
             full_in = {k: v.to(dev) for k, v in synth_inputs(1, S, seed=1).items()}
             line["gpu_torch_baseline"] = gpu_torch_baseline(model, full_in, cfg, dev, ours)
         except Exception as ex:   # a baseline leg must never cost the product line
-            line["gpu_torch_baseline"] = {"unavailable": repr(ex)[:300]}
+            import traceback
+            line["gpu_torch_baseline"] = {"unavailable": repr(ex)[:300], "where": traceback.format_exc()[-600:]}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
