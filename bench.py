@@ -361,7 +361,7 @@ def main():
     tp = os.path.join(ROOT, "profiles", "attn_traffic.json")
     if os.path.exists(tp):
         traffic = json.load(open(tp)).get(f"S{S}") if Bm == 1 else None
-    roofline = {"kernel": "ovg::attn3_kernel (global attention)", "bound": "tensor", "achieved": achieved, "peak": peak_tf,
+    roofline = {"kernel": "ovg::attn1_kernel (global attention)", "bound": "tensor", "achieved": achieved, "peak": peak_tf,
                 "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": traffic, "peak_source": peak_src,
                 "launches_timed": len(att_ms), "avg_launch_ms": att_avg,
                 "share_of_step": sum(att_ms) / args.steps / ms_step,

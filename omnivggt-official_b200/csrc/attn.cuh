@@ -4,9 +4,7 @@
 //
 // q is pre-scaled by (1/sqrt(64))*log2(e) in the QKV GEMM epilogue, so probabilities are exp2(s - m).
 //
-// attn4_kernel (end of this file) is the product kernel; attn1_kernel is the round-1 kernel kept for one A/B run.
-//
-// Online softmax with a stale reference and lazy rescaling (both kernels): P(j) = exp2(S - m_ref) is computed against
+// Online softmax with a stale reference and lazy rescaling: P(j) = exp2(S - m_ref) is computed against
 // the reference left by earlier steps while this step's row maximum is gathered in the same pass; O / l are rescaled
 // (and the chunk redone from the S values still in registers) only when the maximum exceeds the reference by > 8 (log2
 // units) -- exact, the reference cancels in O / l, and P stays <= 256.
@@ -55,6 +53,9 @@ __device__ __forceinline__ float2 exp2_poly2(float2 x) {
   o.y = __int_as_float(__float_as_int(t.y) * 8388608 + __float_as_int(p.y));
   return o;
 }
+#ifndef OVG_ATT_LATE_WAIT
+#define OVG_ATT_LATE_WAIT 1   // P chunks computed before the wait for PV(j-1) (0: wait before the first store, as in round 1)
+#endif
 #ifndef OVG_ATT_EMU_PAIRS
 #define OVG_ATT_EMU_PAIRS 4   // of every 16 element pairs, how many take the polynomial path (0 = all MUFU); 4 measured best
 #endif
@@ -142,319 +143,6 @@ attn1_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
       int s = 0;
       uint32_t ph = 0;
       for (int j = 0; j < nkv; ++j) {
-        mbar_wait(&k_empty[s], ph ^ 1);
-        mbar_expect_tx(&k_full[s], ATT_TILE_BYTES);
-        tma_load_3d(sK + s * ATT_TILE_BYTES, &tmK, &k_full[s], 0, j * 128, bh);
-        mbar_wait(&v_empty[s], ph ^ 1);
-        mbar_expect_tx(&v_full[s], ATT_TILE_BYTES);
-        tma_load_3d(sV + s * ATT_TILE_BYTES, &tmV, &v_full[s], 0, j * 128, bh);
-        if (++s == NS) {
-          s = 0;
-          ph ^= 1;
-        }
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
-      constexpr uint32_t idesc_pv = make_idesc_bf16(128, 64, 0, 1);  // B (=V) is MN-major
-      const uint32_t tS = tmem_base;
-      const uint32_t tP = tmem_base + 128;
-      const uint32_t tO = tmem_base + 192;
-      const uint64_t qdesc = make_sw128_desc(smem_u32(sQ));
-      const uint64_t kdesc0 = make_sw128_desc(smem_u32(sK));
-      const uint64_t vdesc0 = make_sw128_desc(smem_u32(sV));
-      constexpr uint64_t kStageStep = ATT_TILE_BYTES >> 4;
-      auto issue_S = [&](int stage) {
-        const uint64_t bdesc = kdesc0 + stage * kStageStep;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) umma_ss(tS, qdesc + 2 * k, bdesc + 2 * k, idesc_s, k > 0 ? 1u : 0u);
-        umma_commit(s_full);
-      };
-      auto issue_PV = [&](int stage, int j) {
-        const uint64_t bdesc = vdesc0 + stage * kStageStep;
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
-          umma_ts(tO, tP + 8 * k, bdesc + static_cast<uint64_t>(k) * (2048 >> 4), idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
-        umma_commit(o_ready);
-      };
-      mbar_wait(q_full, 0);
-      mbar_wait(&k_full[0], 0);
-      tc_fence_after();
-      issue_S(0);
-      umma_commit(&k_empty[0]);
-      int s = 0, sn = 1 % NS;
-      uint32_t ph = 0, phn = (NS == 1) ? 1u : 0u;
-      for (int j = 0; j < nkv; ++j) {
-        if (j + 1 < nkv) {              // S(j+1) as soon as the softmax warps hold S(j) in registers
-          mbar_wait(&k_full[sn], phn);
-          mbar_wait(s_taken, j & 1);
-          tc_fence_after();
-          issue_S(sn);
-          umma_commit(&k_empty[sn]);
-        }
-        mbar_wait(&v_full[s], ph);
-        mbar_wait(p_full, j & 1);
-        tc_fence_after();
-        issue_PV(s, j);
-        umma_commit(&v_empty[s]);
-        s = sn;
-        ph = phn;
-        if (++sn == NS) {
-          sn = 0;
-          phn ^= 1;
-        }
-      }
-    }
-  } else if (warp >= 4) {
-    reg_alloc<208>();
-    const int quarter = warp & 3;
-    const int r = quarter * 32 + lane;
-    const int qrow = q0 + r;
-    const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
-    const uint32_t tS = tmem_base + lane_off;
-    const uint32_t tP = tmem_base + 128 + lane_off;
-    const uint32_t tO = tmem_base + 192 + lane_off;
-    float m_used = -INFINITY;
-    float l = 0.f;
-    for (int j = 0; j < nkv; ++j) {
-      const int kv_valid = min(128, p.n - j * 128);
-      mbar_wait(s_full, j & 1);
-      tc_fence_after();
-      uint32_t raw[128];
-      tmem_ld32(tS, raw);
-      tmem_ld32(tS + 32, raw + 32);
-      tmem_ld32(tS + 64, raw + 64);
-      tmem_ld32(tS + 96, raw + 96);
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(s_taken);
-      if (kv_valid != 128) {
-#pragma unroll
-        for (int i = 0; i < 128; ++i)
-          if (i >= kv_valid) raw[i] = 0xff800000u;
-      }
-      // stale-reference softmax step (see the file header)
-      float2 acc = make_float2(0.f, 0.f);
-      bool slow = (j == 0);
-      float m_new = m_used;
-      if (j > 0) {
-        const float2 negm = make_float2(-m_used, -m_used);
-        float mx0 = -INFINITY, mx1 = -INFINITY;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          uint32_t pk[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float r0 = __uint_as_float(raw[c * 32 + 2 * i]), r1 = __uint_as_float(raw[c * 32 + 2 * i + 1]);
-            if (i & 1) mx1 = fmaxf(fmaxf(mx1, r0), r1); else mx0 = fmaxf(fmaxf(mx0, r0), r1);
-            float2 x = fadd2(make_float2(r0, r1), negm);
-            if (i >= 16 - OVG_ATT_EMU_PAIRS) {
-              x = exp2_poly2(x);
-            } else {
-              x.x = ex2_approx(x.x);
-              x.y = ex2_approx(x.y);
-            }
-            acc = fadd2(acc, x);
-            pk[i] = pack_bf16(x.x, x.y);
-          }
-          if (c == 0) {
-            mbar_wait(o_ready, (j - 1) & 1);   // PV(j-1) complete: P buffer reusable, O stable
-            tc_fence_after();
-          }
-          tmem_st16(tP + c * 16, pk);
-        }
-        m_new = fmaxf(m_used, fmaxf(mx0, mx1));
-        slow = __any_sync(0xffffffffu, (m_new - m_used) > 8.0f);
-      }
-      if (slow) {
-        if (j == 0) {
-          float mx0 = -INFINITY, mx1 = -INFINITY;
-#pragma unroll
-          for (int i = 0; i < 128; i += 4) {
-            mx0 = fmaxf(fmaxf(mx0, __uint_as_float(raw[i])), __uint_as_float(raw[i + 1]));
-            mx1 = fmaxf(fmaxf(mx1, __uint_as_float(raw[i + 2])), __uint_as_float(raw[i + 3]));
-          }
-          m_used = fmaxf(mx0, mx1);
-        } else {
-          const bool need = (m_new - m_used) > 8.0f;
-          const float alpha = need ? ex2_approx(m_used - m_new) : 1.0f;
-          if (need) {
-            m_used = m_new;
-            l *= alpha;
-          }
-          tmem_st_wait();
-#pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            uint32_t o[32];
-            tmem_ld32(tO + c * 32, o);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            tmem_st32(tO + c * 32, o);
-          }
-        }
-        const float2 negm = make_float2(-m_used, -m_used);
-        acc = make_float2(0.f, 0.f);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          uint32_t pk[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            float2 x = make_float2(__uint_as_float(raw[c * 32 + 2 * i]), __uint_as_float(raw[c * 32 + 2 * i + 1]));
-            x = fadd2(x, negm);
-            x.x = ex2_approx(x.x);
-            x.y = ex2_approx(x.y);
-            acc = fadd2(acc, x);
-            pk[i] = pack_bf16(x.x, x.y);
-          }
-          tmem_st16(tP + c * 16, pk);
-        }
-      }
-      l += acc.x + acc.y;
-      tmem_st_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(p_full);
-    }
-    // ---- epilogue: O / l -> bf16 -> out[b, qrow, head*64 .. +64)
-    mbar_wait(o_ready, (nkv - 1) & 1);
-    tc_fence_after();
-    const float inv = 1.0f / l;
-    uint32_t o[64];
-    tmem_ld32(tO, o);
-    tmem_ld32(tO + 32, o + 32);
-    tmem_ld_wait();
-    if (qrow < p.n) {
-      uint4* dst = reinterpret_cast<uint4*>(p.out + (static_cast<long long>(blockIdx.z) * p.n + qrow) * p.C + head * 64);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        uint4 w;
-        w.x = pack_bf16(__uint_as_float(o[8 * i + 0]) * inv, __uint_as_float(o[8 * i + 1]) * inv);
-        w.y = pack_bf16(__uint_as_float(o[8 * i + 2]) * inv, __uint_as_float(o[8 * i + 3]) * inv);
-        w.z = pack_bf16(__uint_as_float(o[8 * i + 4]) * inv, __uint_as_float(o[8 * i + 5]) * inv);
-        w.w = pack_bf16(__uint_as_float(o[8 * i + 6]) * inv, __uint_as_float(o[8 * i + 7]) * inv);
-        dst[i] = w;
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, 256);
-  }
-}
-
-
-
-// ---------------------------------------------------------------------------------------------------------------------
-// attn4_kernel: attn1_kernel's structure (one 128-row tile per CTA, two CTAs per SM, whole S row in registers, separate
-// P buffer so that S(j+1) runs under the softmax of step j) with a PACKED HALF-PRECISION softmax:
-//   x = S - m_ref            FADD2 (fp32 pair)
-//   h = f16x2(x)             one F2FP per pair           -- |x| 2^-12 absolute: 8x finer than a bf16 P could resolve
-//   P = ex2.approx.f16x2(h)  one issue slot per pair, result is already the packed A operand of the PV MMA
-// so a pair costs 3 issue slots instead of 6 (sub, 2 x MUFU, pack, running max, row sum), the running maximum is not tracked
-// at all, and P carries 11 instead of 8 significant bits.  What replaces the dropped pieces:
-//   * overflow test: the reference m_ref may be stale by less than ONE log2 unit, i.e. P < 2 <=> bit 14 of every f16 is clear;
-//     one 3-input LOP3 per two pairs ORs the packed results, a set bit 14 anywhere in the warp takes the exact slow path
-//     (row maximum from the S row still in registers, O / l rescaled, P recomputed in fp32).  The first KV step always does.
-//   * row sum: f16 tree over 8 packed registers (values < 2, sums < 16, unbiased rounding at 2^-11), then one fp32 FADD2.
-//   * P below 2^-14 is an f16 subnormal (absolute resolution 2^-24): the total error of the tail is < n 2^-25 of the
-//     largest term -- 1e-3 for the 33 K keys of a 24-view global attention -- instead of a relative 2^-9 on every term.
-// The PV MMA mixes operand formats: A = P (f16, from TMEM), B = V (bf16, smem), fp32 accumulate.
-// OVG_ATT_EMU_PAIRS of every 16 pairs still go through the fp32 Cody-Waite polynomial (FMA pipes) instead of the MUFU.
-__device__ __forceinline__ uint32_t pack_f16(float lo, float hi) {
-  uint32_t d;
-  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
-  return d;
-}
-__device__ __forceinline__ uint32_t ex2_f16x2(uint32_t h) {
-  uint32_t d;
-  asm("ex2.approx.f16x2 %0, %1;" : "=r"(d) : "r"(h));
-  return d;
-}
-__device__ __forceinline__ uint32_t hadd2(uint32_t a, uint32_t b) {
-  uint32_t d;
-  asm("add.rn.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
-  return d;
-}
-__device__ __forceinline__ float2 f16x2_to_f32x2(uint32_t h) {
-  float2 f;
-  asm("{\n .reg .b16 l, h;\n mov.b32 {l, h}, %2;\n cvt.f32.f16 %0, l;\n cvt.f32.f16 %1, h;\n}\n" : "=f"(f.x), "=f"(f.y) : "r"(h));
-  return f;
-}
-#ifndef OVG_ATT4_EMU_PAIRS
-#define OVG_ATT4_EMU_PAIRS 0
-#endif
-
-__global__ void __launch_bounds__(ATT1_THREADS, 2)
-attn4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-             const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
-  constexpr int NS = ATT1_KV_STAGES;
-  extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* sQ = smem;
-  uint8_t* sK = smem + ATT_TILE_BYTES;
-  uint8_t* sV = sK + NS * ATT_TILE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + NS * ATT_TILE_BYTES);
-  uint64_t* q_full = bars;             // [1]
-  uint64_t* k_full = bars + 1;         // [NS]
-  uint64_t* k_empty = k_full + NS;     // [NS]
-  uint64_t* v_full = k_empty + NS;     // [NS]
-  uint64_t* v_empty = v_full + NS;     // [NS]
-  uint64_t* s_full = v_empty + NS;     // [1]
-  uint64_t* p_full = s_full + 1;       // [1]
-  uint64_t* o_ready = p_full + 1;      // [1]
-  uint64_t* s_taken = o_ready + 1;     // [1]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_taken + 1);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * 128;
-  const int head = blockIdx.y;
-  const int bh = blockIdx.z * p.heads + head;
-  const int nkv = (p.n + 127) / 128;
-
-  if (warp == 0 && lane == 0) {
-    if (smem_u32(smem) & 1023u) {
-      printf("ovg attn4: dynamic shared memory base is not 1024-byte aligned\n");
-      __trap();
-    }
-    tma_prefetch_desc(&tmQ);
-    tma_prefetch_desc(&tmK);
-    tma_prefetch_desc(&tmV);
-    mbar_init(q_full, 1);
-    mbar_init(s_full, 1);
-    mbar_init(p_full, 4);
-    mbar_init(o_ready, 1);
-    mbar_init(s_taken, 4);
-    for (int i = 0; i < NS; ++i) {
-      mbar_init(&k_full[i], 1);
-      mbar_init(&k_empty[i], 1);
-      mbar_init(&v_full[i], 1);
-      mbar_init(&v_empty[i], 1);
-    }
-    fence_barrier_init();
-  }
-  if (warp == 1) {
-    tmem_alloc(tmem_slot, 256);
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  // register budget: launch allocation 128 * 256 = 32768 per CTA; after the split 128*40 + 128*208 = 31744
-  if (warp < 4) reg_dealloc<40>();
-  if (warp == 0) {
-    if (lane == 0) {
-      mbar_expect_tx(q_full, ATT_TILE_BYTES);
-      tma_load_3d(sQ, &tmQ, q_full, 0, q0, bh);
-      int s = 0;
-      uint32_t ph = 0;
-      for (int j = 0; j < nkv; ++j) {
         mbar_wait_quiet(&k_empty[s], ph ^ 1);
         mbar_expect_tx(&k_full[s], ATT_TILE_BYTES);
         tma_load_3d(sK + s * ATT_TILE_BYTES, &tmK, &k_full[s], 0, j * 128, bh);
@@ -470,9 +158,7 @@ attn4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
-      // P . V: A = P in f16 (format 0) from TMEM, B = V in bf16 (format 1), MN-major, fp32 accumulate
-      constexpr uint32_t idesc_pv = (1u << 4) | (0u << 7) | (1u << 10) | (1u << 16) | (static_cast<uint32_t>(64 >> 3) << 17) |
-                                    (static_cast<uint32_t>(128 >> 4) << 24);
+      constexpr uint32_t idesc_pv = make_idesc_bf16(128, 64, 0, 1);  // B (=V) is MN-major
       const uint32_t tS = tmem_base;
       const uint32_t tP = tmem_base + 128;
       const uint32_t tO = tmem_base + 192;
@@ -530,7 +216,7 @@ attn4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
     const uint32_t tS = tmem_base + lane_off;
     const uint32_t tP = tmem_base + 128 + lane_off;
     const uint32_t tO = tmem_base + 192 + lane_off;
-    float m_ref = -INFINITY;
+    float m_used = -INFINITY;
     float l = 0.f;
     for (int j = 0; j < nkv; ++j) {
       const int kv_valid = min(128, p.n - j * 128);
@@ -548,55 +234,71 @@ attn4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
       if (kv_valid != 128) {
 #pragma unroll
         for (int i = 0; i < 128; ++i)
-          if (i >= kv_valid) raw[i] = 0xff800000u;     // -inf: f16 -inf -> ex2 = +0
+          if (i >= kv_valid) raw[i] = 0xff800000u;
       }
+      // stale-reference softmax step (see the file header)
       float2 acc = make_float2(0.f, 0.f);
       bool slow = (j == 0);
+      float m_new = m_used;
       if (j > 0) {
-        const float2 negm = make_float2(-m_ref, -m_ref);
-        uint32_t orv = 0;
+        const float2 negm = make_float2(-m_used, -m_used);
+        float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+        // The P buffer may only be overwritten once PV(j-1) has read it (o_ready).  PV(j-1) is issued when this step
+        // starts, so waiting before the first P store exposed its whole latency: ncu attributed 24% of the fast pass to
+        // that wait.  The packed results of the first OVG_ATT_LATE_WAIT chunks are held in registers instead and the wait
+        // is taken one or two chunks (~500 - 1000 clocks) later, when the MMA has long finished.
+        uint32_t held[OVG_ATT_LATE_WAIT > 0 ? 16 * OVG_ATT_LATE_WAIT : 1];
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           uint32_t pk[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            float2 x = fadd2(make_float2(__uint_as_float(raw[c * 32 + 2 * i]), __uint_as_float(raw[c * 32 + 2 * i + 1])), negm);
-            if (i >= 16 - OVG_ATT4_EMU_PAIRS) {
+            const float r0 = __uint_as_float(raw[c * 32 + 2 * i]), r1 = __uint_as_float(raw[c * 32 + 2 * i + 1]);
+            if (i & 1) mx1 = fmaxf(fmaxf(mx1, r0), r1); else mx0 = fmaxf(fmaxf(mx0, r0), r1);
+            float2 x = fadd2(make_float2(r0, r1), negm);
+            if (i >= 16 - OVG_ATT_EMU_PAIRS) {
               x = exp2_poly2(x);
-              pk[i] = pack_f16(x.x, x.y);
             } else {
-              pk[i] = ex2_f16x2(pack_f16(x.x, x.y));
+              x.x = ex2_approx(x.x);
+              x.y = ex2_approx(x.y);
             }
+            acc = fadd2(acc, x);
+            pk[i] = pack_bf16(x.x, x.y);
           }
+          if (c < OVG_ATT_LATE_WAIT) {
 #pragma unroll
-          for (int i = 0; i < 16; i += 2) orv |= pk[i] | pk[i + 1];
-          if (c == 0) {
+            for (int i = 0; i < 16; ++i) held[c * 16 + i] = pk[i];
+            continue;
+          }
+          if (c == OVG_ATT_LATE_WAIT) {
             mbar_wait_quiet(o_ready, (j - 1) & 1);   // PV(j-1) complete: P buffer reusable, O stable
             tc_fence_after();
+#pragma unroll
+            for (int h = 0; h < OVG_ATT_LATE_WAIT; ++h) tmem_st16(tP + h * 16, held + h * 16);
           }
           tmem_st16(tP + c * 16, pk);
-          // row sum: f16 tree over 8 packed registers (16 probabilities < 2 each), then fp32
-#pragma unroll
-          for (int g = 0; g < 2; ++g) {
-            const uint32_t s01 = hadd2(pk[8 * g + 0], pk[8 * g + 1]), s23 = hadd2(pk[8 * g + 2], pk[8 * g + 3]);
-            const uint32_t s45 = hadd2(pk[8 * g + 4], pk[8 * g + 5]), s67 = hadd2(pk[8 * g + 6], pk[8 * g + 7]);
-            acc = fadd2(acc, f16x2_to_f32x2(hadd2(hadd2(s01, s23), hadd2(s45, s67))));
-          }
         }
-        slow = __any_sync(0xffffffffu, (orv & 0x40004000u) != 0u);   // some P >= 2 (or inf / nan): reference too stale
+        m_new = fmaxf(m_used, fmaxf(mx0, mx1));
+        slow = __any_sync(0xffffffffu, (m_new - m_used) > 8.0f);
       }
       if (slow) {
-        float mx0 = -INFINITY, mx1 = -INFINITY;
+        if (j == 0) {
+          float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
-        for (int i = 0; i < 128; i += 4) {
-          mx0 = fmaxf(fmaxf(mx0, __uint_as_float(raw[i])), __uint_as_float(raw[i + 1]));
-          mx1 = fmaxf(fmaxf(mx1, __uint_as_float(raw[i + 2])), __uint_as_float(raw[i + 3]));
-        }
-        const float m_new = fmaxf(m_ref, fmaxf(mx0, mx1));
-        if (j > 0) {
-          const float alpha = ex2_approx(m_ref - m_new);     // 1 for rows whose maximum did not grow
-          l *= alpha;
-          tmem_st_wait();               // the P stores of the fast pass are re-issued below
+          for (int i = 0; i < 128; i += 4) {
+            mx0 = fmaxf(fmaxf(mx0, __uint_as_float(raw[i])), __uint_as_float(raw[i + 1]));
+            mx1 = fmaxf(fmaxf(mx1, __uint_as_float(raw[i + 2])), __uint_as_float(raw[i + 3]));
+          }
+          m_used = fmaxf(mx0, mx1);
+        } else {
+          const bool need = (m_new - m_used) > 8.0f;
+          const float alpha = need ? ex2_approx(m_used - m_new) : 1.0f;
+          if (need) {
+            m_used = m_new;
+            l *= alpha;
+          }
+          tmem_st_wait();
 #pragma unroll
           for (int c = 0; c < 2; ++c) {
             uint32_t o[32];
@@ -607,8 +309,7 @@ attn4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
             tmem_st32(tO + c * 32, o);
           }
         }
-        m_ref = m_new;
-        const float2 negm = make_float2(-m_ref, -m_ref);
+        const float2 negm = make_float2(-m_used, -m_used);
         acc = make_float2(0.f, 0.f);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
@@ -620,7 +321,7 @@ attn4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
             x.x = ex2_approx(x.x);
             x.y = ex2_approx(x.y);
             acc = fadd2(acc, x);
-            pk[i] = pack_f16(x.x, x.y);
+            pk[i] = pack_bf16(x.x, x.y);
           }
           tmem_st16(tP + c * 16, pk);
         }
@@ -659,5 +360,7 @@ attn4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
     tmem_dealloc(tmem_base, 256);
   }
 }
+
+
 
 }  // namespace ovg

@@ -420,7 +420,6 @@ int ovg_attention(const void* q, const void* k, const void* v, void* out, int ba
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   CUtensorMap tq, tk, tv;
   const unsigned long long bh = static_cast<unsigned long long>(batch) * heads;
-  static const int attn_kernel = [] { const char* e = getenv("OVG_ATTN_KERNEL"); return e ? atoi(e) : 4; }();   // A/B run only
   int rc = get_map(q, 64, n, bh, 64, 128, &tq);
   if (rc) return rc;
   rc = get_map(k, 64, n, bh, 64, 128, &tk);
@@ -431,16 +430,11 @@ int ovg_attention(const void* q, const void* k, const void* v, void* out, int ba
   if (once.needed()) {
     OVG_CUDA(cudaFuncSetAttribute(ovg::attn1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ovg::ATT1_SMEM_BYTES));
     OVG_CUDA(cudaFuncSetAttribute(ovg::attn1_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    OVG_CUDA(cudaFuncSetAttribute(ovg::attn4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ovg::ATT1_SMEM_BYTES));
-    OVG_CUDA(cudaFuncSetAttribute(ovg::attn4_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     once.mark_done();
   }
   ovg::AttnParams p{n, heads, heads * 64, reinterpret_cast<__nv_bfloat16*>(out), g_attn_prof};
   dim3 grid1((n + 127) / 128, heads, batch);
-  if (attn_kernel == 1)
-    ovg::attn1_kernel<<<grid1, ovg::ATT1_THREADS, ovg::ATT1_SMEM_BYTES, st>>>(tq, tk, tv, p);
-  else
-    ovg::attn4_kernel<<<grid1, ovg::ATT1_THREADS, ovg::ATT1_SMEM_BYTES, st>>>(tq, tk, tv, p);
+  ovg::attn1_kernel<<<grid1, ovg::ATT1_THREADS, ovg::ATT1_SMEM_BYTES, st>>>(tq, tk, tv, p);
   return post_launch("ovg_attention");
 }
 

@@ -1,6 +1,9 @@
 """The block-level kernels at cfg2 shapes, one launch each inside a cudaProfiler range (for `ncu --set full`):
    0 qkv fused (LN + RoPE epilogue)   1 proj (residual)   2 fc1 (GELU)   3 fc2 (residual)   4 global attention   5 layernorm
    6 DPT tail (3x3 conv 128->32 + 1x1 + activations, 8 frames @ 518^2)   7 bilinear upsampling 296^2 -> 518^2 (128 ch)
+and the modality gather / scatter kernels at the cfg5 shapes (24 views, 6 depth views):
+   8 assemble_tokens   9 inject_snapshot (with bf16 slot)   10 depth_stats   11 depth_im2col   12 image_im2col
+NCU_ONLY=attn restricts the profiled range to the global attention.
 """
 import os
 import sys
@@ -53,7 +56,37 @@ xu = torch.empty(Fr, hh + 2, ww + 2, 128, device=dev, dtype=BF16)
 tx, ty = rn(ww, 64), rn(hh, 64)
 
 
+# ---- modality gather / scatter at cfg5 shapes: K = 24 frames, depth aux on 6 of them
+K5, P5 = 24, 1369
+patch5 = rn(K5, P5, C)
+x5 = torch.empty(K5, T, C, device=dev)
+cam_tok, reg_tok, inj0, placeholder = rn(2, C), rn(2, 4, C), rn(K5, C), rn(C)
+has_depth = torch.zeros(K5, dtype=torch.int32, device=dev)
+didx = [0, 3, 4, 9, 15, 22]
+has_depth[didx] = 1
+slot5 = torch.empty(K5 * T, 2 * C, device=dev, dtype=BF16)
+depth5 = 0.5 + 4 * torch.rand(1, K5, 518, 518, device=dev, generator=g)
+mask5 = (torch.rand(1, K5, 518, 518, device=dev, generator=g) > 0.2).float()
+idx5 = torch.tensor(didx, dtype=torch.int32, device=dev)
+scratch5 = torch.zeros(128 * 2, dtype=torch.float64, device=dev)
+cols5 = torch.empty(len(didx) * P5, 392, device=dev, dtype=BF16)
+img5 = torch.rand(K5, 3, 518, 518, device=dev, generator=g)
+icol5 = torch.empty(K5 * P5, 592, device=dev, dtype=BF16)
+ONLY = os.environ.get("NCU_ONLY", "")
+
+
 def run():
+    if ONLY == "attn":
+        ops.attention(q, k, v, o, 1, 16, M)
+        return
+    run_blocks()
+    ops.assemble_tokens(x5, patch5, cam_tok, reg_tok, inj0, placeholder, has_depth, K5, K5, T, 4, C)
+    ops.inject_snapshot(x5.view(K5 * T, C), inj0, slot5, None, K5, T, C, 0)
+    ops.depth_im2col(depth5, mask5, idx5, scratch5, cols5, 1, K5, len(didx), 518, 518, 14)
+    ops.image_im2col(img5, (0.485, 0.456, 0.406), (0.229, 0.224, 0.225), icol5, K5, 518, 518, 14)
+
+
+def run_blocks():
     ops.qkv_proj(a, wqkv, bqkv, ones, zeros, ones, zeros, q, k, v, ntok=M, T=T, nspecial=5, wp=37, rope_cos=cos, rope_sin=sin)
     ops.linear_resid(a, wproj, bproj, gamma, x)
     ops.linear_bf16(a, w1, b1, act=ops.L.ACT_GELU, out=hid)
