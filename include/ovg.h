@@ -103,7 +103,8 @@ int ovg_inject_snapshot(float* x, const float* inj, void* slot, float* cam_out, 
 
 /* Depth modality: masked per-scene mean over the selected views, then [depth/(mean+1e-8)*mask, mask] im2col rows
  * (2*patch*patch wide, row stride ldc) for the patch-embedding GEMM (omnivggt_aggregator.py:107-128,:189-199;
- * layers/patch_embed.py:65-77).  scratch: B * 128 * 2 doubles. */
+ * layers/patch_embed.py:65-77).  scratch: OVG_DEPTH_SCRATCH_DOUBLES(B) doubles of device memory. */
+#define OVG_DEPTH_SCRATCH_DOUBLES(B) ((B) * (2 * 1024 + 1))
 int ovg_depth_im2col(const float* depth, const float* mask, const int* idx, double* scratch, void* cols, int ldc,
                      int B, int S, int Sd, int H, int W, int patch, void* stream);
 
@@ -141,6 +142,95 @@ int ovg_unproject_depth(const float* depth, const float* intrinsic, const float*
 #define OVG_PERCENTILE_WORKSPACE_BYTES (6 * 8 + 512 * 4 + 4 * 4)
 int ovg_conf_percentile_mask(const float* conf, long long n, float percent, float floor_, void* workspace,
                              unsigned char* mask, float* threshold_out, unsigned long long* count_out, void* stream);
+
+/* ======================================================================================================================
+ * Runtime: the launch SEQUENCES of the hot path behind handles, so that a host in any language runs the path with three
+ * calls and raw device pointers.  Weight pointers refer to device memory in kernel layout (bf16
+ * [N, K] matrices, fp32 vectors) owned by the caller and must stay valid for the life of the handle; descriptors are copied.
+ * No entry point allocates device memory: the caller passes a 256-byte aligned workspace of ovg_*_workspace_bytes().
+ * ====================================================================================================================== */
+typedef struct ovg_block_weights {           /* one pre-LN transformer block, reference layers/block.py:27-107 */
+  const float* ln1_w; const float* ln1_b;
+  const void* w_qkv; const float* b_qkv;     /* bf16 [3C, C] */
+  const float* qn_w; const float* qn_b; const float* kn_w; const float* kn_b;   /* q/k LayerNorm(64); all NULL for DINOv2 blocks */
+  const void* w_proj; const float* b_proj; const float* g1;                     /* bf16 [C, C]; LayerScale gamma */
+  const float* ln2_w; const float* ln2_b;
+  const void* w_fc1; const float* b_fc1; const void* w_fc2; const float* b_fc2; const float* g2;
+} ovg_block_weights;
+
+/* Aggregator: token assembly, depth / camera modality injection, depth x (frame block, global block), kept intermediates.
+ * reference models/omnivggt_aggregator.py:130-305, models/aggregator.py:312-341. */
+typedef struct ovg_aggregator_desc {
+  int C; int registers; int depth; int patch;
+  const ovg_block_weights* frame_blocks;     /* host array [depth] */
+  const ovg_block_weights* global_blocks;    /* host array [depth] */
+  const float* cam_tok; const float* reg_tok; const float* placeholder;          /* [2,C], [2,registers,C], [C] */
+  const void* depth_w; const float* depth_b;                                      /* bf16 [C, 2*patch*patch], fp32 [C] */
+  const float* ones_c;                                                            /* fp32 [C] of ones */
+  int keep_layers[4];                                                             /* layers whose outputs feed the DPT heads */
+} ovg_aggregator_desc;
+typedef struct ovg_aggregator ovg_aggregator;
+int ovg_aggregator_create(const ovg_aggregator_desc* desc, ovg_aggregator** out);
+void ovg_aggregator_destroy(ovg_aggregator* h);
+long long ovg_aggregator_workspace_bytes(const ovg_aggregator* h, int B, int S, int H, int W, int n_depth);
+/* patch_tokens fp32 [B*S, P, C]; inj fp32 [depth+1, B*S, C] (camera injection vectors, omnivggt_aggregator.py:172-179,:273-287);
+ * depth / mask fp32 [B,S,H,W] and depth_idx device int[n_depth] (n_depth = 0: no depth aux); rope tables fp32 [maxpos, 16];
+ * slots: host array of 4 device pointers, bf16 [B*S, T, 2C] each (frame half | global half); cam_out fp32 [B*S, 2C]. */
+int ovg_aggregator_forward(ovg_aggregator* h, const float* patch_tokens, const float* inj, const float* depth, const float* mask,
+                           const int* depth_idx, int n_depth, const float* rope_cos, const float* rope_sin, int maxpos, int B,
+                           int S, int H, int W, void* workspace, long long workspace_bytes, void* const* slots, float* cam_out,
+                           void* stream);
+
+/* Frozen DINOv2 patchifier on the same kernels: reference layers/vision_transformer.py:214-271. */
+typedef struct ovg_dino_desc {
+  int C; int registers; int depth; int patch; int kpad;      /* kpad: 3*patch*patch rounded up to a multiple of 8 */
+  const ovg_block_weights* blocks;                           /* host array [depth] */
+  const void* w_patch; const float* b_patch;                 /* bf16 [C, kpad] (zero padded), fp32 [C] */
+  const float* norm_w; const float* norm_b; const float* ones_c;
+} ovg_dino_desc;
+typedef struct ovg_dino ovg_dino;
+int ovg_dino_create(const ovg_dino_desc* desc, ovg_dino** out);
+void ovg_dino_destroy(ovg_dino* h);
+long long ovg_dino_workspace_bytes(const ovg_dino* h, int K, int H, int W);
+/* images fp32 [K,3,H,W] in [0,1]; base_tokens fp32 [1+registers+P, C] = [cls + pos0, registers, pos_patches];
+ * mean3 / std3: HOST float[3]; patch_tokens_out fp32 [K, P, C] (x_norm_patchtokens). */
+int ovg_dino_forward(ovg_dino* h, const float* images, const float* base_tokens, const float* mean3, const float* std3, int K,
+                     int H, int W, void* workspace, long long workspace_bytes, float* patch_tokens_out, void* stream);
+
+/* One DPT head (depth or point): reference heads/dpt_head.py:128-304, heads/head_act.py:61-125. */
+typedef struct ovg_dpt_fusion {
+  const void* rcu1[4];     /* resConfUnit1: conv1 w (bf16 [f, 9f]), conv1 b (fp32), conv2 w, conv2 b; all NULL for refinenet4 */
+  const void* rcu2[4];     /* resConfUnit2 */
+  const void* oc_w; const float* oc_b;   /* out_conv 1x1: bf16 [f, f], fp32 [f] */
+} ovg_dpt_fusion;
+typedef struct ovg_dpt_desc {
+  int C2; int feat; int patch; int outc;                     /* 2*embed_dim, features (256), 14, 2 (depth) / 4 (points) */
+  int oc[4];                                                  /* projection widths (256, 512, 1024, 1024) */
+  const void* proj_w[4]; const float* proj_b[4];              /* 1x1 projections with the LayerNorm affine folded in */
+  const void* up_w[2]; const float* up_b[2];                  /* ConvTranspose k4s4 / k2s2 as [(ky,kx,cout), cin] */
+  const void* down_w; const float* down_b;                    /* Conv k3 s2 p1: bf16 [oc3, 9*oc3] */
+  const void* rn_w[4];                                        /* layerN_rn 3x3, no bias: bf16 [feat, 9*oc] */
+  ovg_dpt_fusion fus[4];                                      /* refinenet1..4 */
+  const void* oc1_w; const float* oc1_b;                      /* output_conv1 3x3 feat -> feat/2 */
+  const void* oc2_w; const float* oc2_b;                      /* output_conv2[0] 3x3 feat/2 -> 32 */
+  const float* w2; const float* b2;                           /* output_conv2[2] 1x1 32 -> outc (fp32) */
+} ovg_dpt_desc;
+typedef struct ovg_dpt ovg_dpt;
+int ovg_dpt_create(const ovg_dpt_desc* desc, ovg_dpt** out);
+void ovg_dpt_destroy(ovg_dpt* h);
+long long ovg_dpt_workspace_bytes(const ovg_dpt* h, int Fc, int H, int W);
+/* One chunk of Fc frames starting at frame f0.  slots: host array of 4 device pointers, bf16 [K, T, C2]; tables: host array of 4
+ * device pointers, fp32 [P, oc[l]] UV position embeddings x0.1 (heads/dpt_head.py:262-272); tx fp32 [W, feat/4], ty fp32
+ * [H, feat/4] separable embedding of the full-resolution stage; head_act 0: exp (depth), 1: inverse-log (points);
+ * preds fp32 [K, H, W, outc-1], conf fp32 [K, H, W] (written for frames f0 .. f0+Fc-1). */
+int ovg_dpt_forward(ovg_dpt* h, const void* const* slots, int T, int nspecial, int f0, int Fc, int H, int W,
+                    const float* const* tables, const float* tx, const float* ty, int head_act, float* preds, float* conf,
+                    void* workspace, long long workspace_bytes, void* stream);
+
+/* Timing hook for bench.py: when enabled, every global-attention launch of ovg_aggregator_forward is bracketed by CUDA events
+ * on its stream; after a synchronize, ovg_runtime_attention_times() returns the elapsed ms of the launches since the enable. */
+void ovg_runtime_time_attention(int enable);
+int ovg_runtime_attention_times(float* ms, int max_n);
 
 #ifdef __cplusplus
 }

@@ -40,6 +40,41 @@ class GemmArgs(C.Structure):
     ]
 
 
+class BlockWeights(C.Structure):
+    """Mirror of ``ovg_block_weights``."""
+    _fields_ = [(n, _vp) for n in ("ln1_w", "ln1_b", "w_qkv", "b_qkv", "qn_w", "qn_b", "kn_w", "kn_b", "w_proj", "b_proj", "g1",
+                                   "ln2_w", "ln2_b", "w_fc1", "b_fc1", "w_fc2", "b_fc2", "g2")]
+
+
+class AggregatorDesc(C.Structure):
+    """Mirror of ``ovg_aggregator_desc``."""
+    _fields_ = [("C", _i), ("registers", _i), ("depth", _i), ("patch", _i),
+                ("frame_blocks", C.POINTER(BlockWeights)), ("global_blocks", C.POINTER(BlockWeights)),
+                ("cam_tok", _vp), ("reg_tok", _vp), ("placeholder", _vp), ("depth_w", _vp), ("depth_b", _vp), ("ones_c", _vp),
+                ("keep_layers", _i * 4)]
+
+
+class DinoDesc(C.Structure):
+    """Mirror of ``ovg_dino_desc``."""
+    _fields_ = [("C", _i), ("registers", _i), ("depth", _i), ("patch", _i), ("kpad", _i),
+                ("blocks", C.POINTER(BlockWeights)), ("w_patch", _vp), ("b_patch", _vp), ("norm_w", _vp), ("norm_b", _vp),
+                ("ones_c", _vp)]
+
+
+class DptFusion(C.Structure):
+    """Mirror of ``ovg_dpt_fusion``."""
+    _fields_ = [("rcu1", _vp * 4), ("rcu2", _vp * 4), ("oc_w", _vp), ("oc_b", _vp)]
+
+
+class DptDesc(C.Structure):
+    """Mirror of ``ovg_dpt_desc``."""
+    _fields_ = [("C2", _i), ("feat", _i), ("patch", _i), ("outc", _i), ("oc", _i * 4),
+                ("proj_w", _vp * 4), ("proj_b", _vp * 4), ("up_w", _vp * 2), ("up_b", _vp * 2), ("down_w", _vp), ("down_b", _vp),
+                ("rn_w", _vp * 4), ("fus", DptFusion * 4), ("oc1_w", _vp), ("oc1_b", _vp), ("oc2_w", _vp), ("oc2_b", _vp),
+                ("w2", _vp), ("b2", _vp)]
+
+
+_pp = C.POINTER(_vp)
 EXPORTS = {
     "ovg_version": (C.c_int, []),
     "ovg_last_error": (C.c_char_p, []),
@@ -57,8 +92,28 @@ EXPORTS = {
     "ovg_pose_decode": (C.c_int, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "ovg_unproject_depth": (C.c_int, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "ovg_conf_percentile_mask": (C.c_int, [_vp, _ll, _f, _f, _vp, _vp, _vp, _vp, _vp]),
+    # ---- runtime (handle-level sequences)
+    "ovg_aggregator_create": (C.c_int, [C.POINTER(AggregatorDesc), _pp]),
+    "ovg_aggregator_destroy": (None, [_vp]),
+    "ovg_aggregator_workspace_bytes": (_ll, [_vp, _i, _i, _i, _i, _i]),
+    "ovg_aggregator_forward": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp, _ll, _pp, _vp, _vp]),
+    "ovg_dino_create": (C.c_int, [C.POINTER(DinoDesc), _pp]),
+    "ovg_dino_destroy": (None, [_vp]),
+    "ovg_dino_workspace_bytes": (_ll, [_vp, _i, _i, _i]),
+    "ovg_dino_forward": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _ll, _vp, _vp]),
+    "ovg_dpt_create": (C.c_int, [C.POINTER(DptDesc), _pp]),
+    "ovg_dpt_destroy": (None, [_vp]),
+    "ovg_dpt_workspace_bytes": (_ll, [_vp, _i, _i, _i]),
+    "ovg_dpt_forward": (C.c_int, [_vp, _pp, _i, _i, _i, _i, _i, _i, _pp, _vp, _vp, _i, _vp, _vp, _vp, _ll, _vp]),
+    "ovg_runtime_time_attention": (None, [_i]),
+    "ovg_runtime_attention_times": (C.c_int, [_vp, _i]),
 }
 PERCENTILE_WORKSPACE_BYTES = 6 * 8 + 512 * 4 + 4 * 4
+
+
+def DEPTH_SCRATCH_DOUBLES(B: int) -> int:
+    """Mirror of OVG_DEPTH_SCRATCH_DOUBLES (include/ovg.h)."""
+    return B * (2 * 1024 + 1)
 
 _lib: Optional[C.CDLL] = None
 _device_ok = False

@@ -53,6 +53,12 @@ __device__ __forceinline__ float2 exp2_poly2(float2 x) {
   o.y = __int_as_float(__float_as_int(t.y) * 8388608 + __float_as_int(p.y));
   return o;
 }
+#ifndef OVG_ATT_NOMAX
+#define OVG_ATT_NOMAX 0        // 1: no running row maximum in the fast pass (overflow is detected on the row sum)
+#endif
+#ifndef OVG_ATT_POLY_INTERLEAVE
+#define OVG_ATT_POLY_INTERLEAVE 0   // 1: the polynomial pairs are every 4th pair instead of the last ones of a chunk
+#endif
 #ifndef OVG_ATT_LATE_WAIT
 #define OVG_ATT_LATE_WAIT 1   // P chunks computed before the wait for PV(j-1) (0: wait before the first store, as in round 1)
 #endif
@@ -243,7 +249,6 @@ attn1_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
       if (j > 0) {
         const float2 negm = make_float2(-m_used, -m_used);
         float mx0 = -INFINITY, mx1 = -INFINITY;
-#pragma unroll
         // The P buffer may only be overwritten once PV(j-1) has read it (o_ready).  PV(j-1) is issued when this step
         // starts, so waiting before the first P store exposed its whole latency: ncu attributed 24% of the fast pass to
         // that wait.  The packed results of the first OVG_ATT_LATE_WAIT chunks are held in registers instead and the wait
@@ -255,9 +260,14 @@ attn1_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const float r0 = __uint_as_float(raw[c * 32 + 2 * i]), r1 = __uint_as_float(raw[c * 32 + 2 * i + 1]);
+            const bool poly = OVG_ATT_POLY_INTERLEAVE ? ((i & 3) == 3 && (i >> 2) < OVG_ATT_EMU_PAIRS) : (i >= 16 - OVG_ATT_EMU_PAIRS);
+#if OVG_ATT_NOMAX
+            if (poly) mx0 = fmaxf(fmaxf(mx0, r0), r1);     // the polynomial's exponent insertion wraps above 2^127: watch its inputs
+#else
             if (i & 1) mx1 = fmaxf(fmaxf(mx1, r0), r1); else mx0 = fmaxf(fmaxf(mx0, r0), r1);
+#endif
             float2 x = fadd2(make_float2(r0, r1), negm);
-            if (i >= 16 - OVG_ATT_EMU_PAIRS) {
+            if (poly) {
               x = exp2_poly2(x);
             } else {
               x.x = ex2_approx(x.x);
@@ -279,8 +289,23 @@ attn1_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
           }
           tmem_st16(tP + c * 16, pk);
         }
+#if OVG_ATT_NOMAX
+        // No running maximum: bf16 P and the fp32 O / l accumulators carry the full fp32 exponent range, so a stale reference
+        // costs no precision until exp2 overflows.  The step is redone (exactly, from the S row in registers) only if the row
+        // sum says a probability came near the top of that range, or a polynomial lane saw an input it cannot represent.
+        slow = __any_sync(0xffffffffu, !(acc.x + acc.y < 1e30f) || (mx0 - m_used) > 100.0f);
+        if (slow) {
+#pragma unroll
+          for (int i = 0; i < 128; i += 4) {
+            mx0 = fmaxf(fmaxf(mx0, __uint_as_float(raw[i])), __uint_as_float(raw[i + 1]));
+            mx1 = fmaxf(fmaxf(mx1, __uint_as_float(raw[i + 2])), __uint_as_float(raw[i + 3]));
+          }
+          m_new = fmaxf(m_used, fmaxf(mx0, mx1));
+        }
+#else
         m_new = fmaxf(m_used, fmaxf(mx0, mx1));
         slow = __any_sync(0xffffffffu, (m_new - m_used) > 8.0f);
+#endif
       }
       if (slow) {
         if (j == 0) {

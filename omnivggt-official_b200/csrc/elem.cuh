@@ -207,27 +207,37 @@ struct DepthParams {
   const float* depth;  // [B, S, H, W]
   const float* mask;   // [B, S, H, W]
   const int* idx;      // [Sd] selected views
-  double* partial;     // [B, NCHUNK, 2] (sum, count)
+  double* partial;     // [B, NCHUNK, 2] (sum, count), then [B] scale factors as float at partial + B * NCHUNK * 2
   __nv_bfloat16* cols;  // [B*Sd*hp*wp, ldc]
   int ldc;
   int B, S, Sd, H, W, patch;
 };
-constexpr int DEPTH_NCHUNK = 128;
+constexpr int DEPTH_NCHUNK = 1024;
 
+// Stage 1: 1024 blocks per scene, each sums a contiguous run of float2 pairs of the selected views (H * W is even: both are
+// multiples of the even patch size).  fp32 partial sums over <= 64 values per thread, combined in double.
 __global__ void __launch_bounds__(256) depth_stats_kernel(const DepthParams p) {
   const int b = blockIdx.y, ch = blockIdx.x;
-  const long long per = static_cast<long long>(p.H) * p.W;
-  const long long total = per * p.Sd;
+  const long long per2 = static_cast<long long>(p.H) * p.W / 2;
+  const long long total2 = per2 * p.Sd;
+  const long long span = (total2 + DEPTH_NCHUNK - 1) / DEPTH_NCHUNK;
+  const long long lo = ch * span, hi = min(lo + span, total2);
   double s = 0.0, cnt = 0.0;
-  for (long long i = static_cast<long long>(ch) * blockDim.x + threadIdx.x; i < total;
-       i += static_cast<long long>(DEPTH_NCHUNK) * blockDim.x) {
-    const int j = static_cast<int>(i / per);
-    const long long off = (static_cast<long long>(b) * p.S + p.idx[j]) * per + (i - j * per);
-    if (p.mask[off] > 0.f) {
-      s += p.depth[off];
-      cnt += 1.0;
+  float fs = 0.f, fc = 0.f;
+  int run = 0;
+  for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+    const int j = static_cast<int>(i / per2);
+    const long long off = (static_cast<long long>(b) * p.S + p.idx[j]) * per2 + (i - j * per2);
+    const float2 m = reinterpret_cast<const float2*>(p.mask)[off];
+    const float2 d = reinterpret_cast<const float2*>(p.depth)[off];
+    if (m.x > 0.f) { fs += d.x; fc += 1.f; }
+    if (m.y > 0.f) { fs += d.y; fc += 1.f; }
+    if (++run == 32) {
+      s += fs; cnt += fc; fs = 0.f; fc = 0.f; run = 0;
     }
   }
+  s += fs;
+  cnt += fc;
   __shared__ double sh[2][256];
   sh[0][threadIdx.x] = s;
   sh[1][threadIdx.x] = cnt;
@@ -245,36 +255,56 @@ __global__ void __launch_bounds__(256) depth_stats_kernel(const DepthParams p) {
   }
 }
 
-__global__ void __launch_bounds__(224) depth_im2col_kernel(const DepthParams p) {
-  const int hp = p.H / p.patch, wp = p.W / p.patch;
-  const int row = blockIdx.x;  // (b, j, py, px)
-  const int px = row % wp, py = (row / wp) % hp, j = (row / (wp * hp)) % p.Sd, b = row / (wp * hp * p.Sd);
-  __shared__ float s_scale;
-  if (threadIdx.x == 0) {
-    double s = 0.0, c = 0.0;
-    for (int i = 0; i < DEPTH_NCHUNK; ++i) {
-      s += p.partial[(static_cast<long long>(b) * DEPTH_NCHUNK + i) * 2 + 0];
-      c += p.partial[(static_cast<long long>(b) * DEPTH_NCHUNK + i) * 2 + 1];
-    }
-    s_scale = c > 0.0 ? 1.0f / (static_cast<float>(s / c) + 1e-8f) : 0.0f;   // no valid pixel -> zeros (:121-122)
+// Stage 2: one block per scene folds the partials in a fixed order -> scale = 1 / (mean + 1e-8), or 0 without a valid pixel.
+__global__ void __launch_bounds__(256) depth_scale_kernel(const DepthParams p) {
+  const int b = blockIdx.x;
+  __shared__ double sh[2][256];
+  double s = 0.0, c = 0.0;
+  for (int i = threadIdx.x; i < DEPTH_NCHUNK; i += 256) {
+    s += p.partial[(static_cast<long long>(b) * DEPTH_NCHUNK + i) * 2 + 0];
+    c += p.partial[(static_cast<long long>(b) * DEPTH_NCHUNK + i) * 2 + 1];
   }
+  sh[0][threadIdx.x] = s;
+  sh[1][threadIdx.x] = c;
   __syncthreads();
-  const int pp = p.patch * p.patch;
-  for (int e = threadIdx.x; e < pp; e += blockDim.x) {
-    const int ky = e / p.patch, kx = e % p.patch;
-    const long long off = ((static_cast<long long>(b) * p.S + p.idx[j]) * p.H + (py * p.patch + ky)) * p.W +
-                          (px * p.patch + kx);
-    const float m = p.mask[off];
-    const float d = p.depth[off] * s_scale * m;
-    __nv_bfloat16* dst = p.cols + static_cast<long long>(row) * p.ldc;
-    dst[e] = __float2bfloat16(d);
-    dst[pp + e] = __float2bfloat16(m);
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      sh[0][threadIdx.x] += sh[0][threadIdx.x + o];
+      sh[1][threadIdx.x] += sh[1][threadIdx.x + o];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    float* scale = reinterpret_cast<float*>(p.partial + static_cast<long long>(p.B) * DEPTH_NCHUNK * 2);
+    scale[b] = sh[1][0] > 0.0 ? 1.0f / (static_cast<float>(sh[0][0] / sh[1][0]) + 1e-8f) : 0.0f;   // no valid pixel -> zeros (:121-122)
+  }
+}
+
+// Stage 3: one block per (scene, selected view, patch row): the 14 image rows are read as coalesced float2 runs, every pair
+// lands in one patch (the patch size is even) and is stored as one bf16x2.
+__global__ void __launch_bounds__(256) depth_im2col_kernel(const DepthParams p) {
+  const int hp = p.H / p.patch, wp = p.W / p.patch;
+  const int py = blockIdx.x % hp, j = (blockIdx.x / hp) % p.Sd, b = blockIdx.x / (hp * p.Sd);
+  const float scale = reinterpret_cast<const float*>(p.partial + static_cast<long long>(p.B) * DEPTH_NCHUNK * 2)[b];
+  const int w2 = p.W / 2, pp = p.patch * p.patch;
+  const long long img = ((static_cast<long long>(b) * p.S + p.idx[j]) * p.H + static_cast<long long>(py) * p.patch) * p.W;
+  const long long row0 = ((static_cast<long long>(b) * p.Sd + j) * hp + py) * wp;
+  for (int e = threadIdx.x; e < p.patch * w2; e += blockDim.x) {
+    const int ky = e / w2, x = (e - ky * w2) * 2;
+    const int px = x / p.patch, kx = x - px * p.patch;
+    const long long off = img + static_cast<long long>(ky) * p.W + x;
+    const float2 m = *reinterpret_cast<const float2*>(p.mask + off);
+    const float2 d = *reinterpret_cast<const float2*>(p.depth + off);
+    __nv_bfloat16* dst = p.cols + (row0 + px) * p.ldc + ky * p.patch + kx;
+    *reinterpret_cast<uint32_t*>(dst) = pack_bf16(d.x * scale * m.x, d.y * scale * m.y);
+    *reinterpret_cast<uint32_t*>(dst + pp) = pack_bf16(m.x, m.y);
   }
 }
 
 // ---------------------------------------------------------------------------------------------------
 // RGB patch im2col for the DINOv2 patch-embedding GEMM (reference layers/patch_embed.py:65-77) with the ImageNet
-// normalisation of models/omnivggt_aggregator.py:143 fused.  One block per patch; cols (c, ky, kx), zero padded to ldc.
+// normalisation of models/omnivggt_aggregator.py:143 fused.  One block per (frame, patch row): 3 x 14 image rows as coalesced
+// float2 runs -> bf16x2 stores into cols (c, ky, kx); columns [3 * patch^2, ldc) are zero padding.
 struct ImageColParams {
   const float* img;   // [K, 3, H, W]
   __nv_bfloat16* cols;
@@ -284,19 +314,23 @@ struct ImageColParams {
 
 __global__ void __launch_bounds__(256) image_im2col_kernel(const ImageColParams p) {
   const int hp = p.H / p.patch, wp = p.W / p.patch;
-  const int row = blockIdx.x;
-  const int px = row % wp, py = (row / wp) % hp, k = row / (wp * hp);
-  const int pp = p.patch * p.patch;
-  __nv_bfloat16* dst = p.cols + static_cast<long long>(row) * p.ldc;
-  for (int e = threadIdx.x; e < p.ldc; e += blockDim.x) {
-    float v = 0.f;
-    if (e < 3 * pp) {
-      const int c = e / pp, r = e - c * pp;
-      const int ky = r / p.patch, kx = r - ky * p.patch;
-      v = (p.img[((static_cast<long long>(k) * 3 + c) * p.H + (py * p.patch + ky)) * p.W + (px * p.patch + kx)] - p.mean[c]) *
-          p.istd[c];
-    }
-    dst[e] = __float2bfloat16(v);
+  const int py = blockIdx.x % hp, k = blockIdx.x / hp;
+  const int w2 = p.W / 2, pp = p.patch * p.patch;
+  const long long row0 = (static_cast<long long>(k) * hp + py) * wp;
+  const int per_c = p.patch * w2;
+  for (int e = threadIdx.x; e < 3 * per_c; e += blockDim.x) {
+    const int c = e / per_c, r = e - c * per_c;
+    const int ky = r / w2, x = (r - ky * w2) * 2;
+    const int px = x / p.patch, kx = x - px * p.patch;
+    const float2 v = *reinterpret_cast<const float2*>(
+        p.img + ((static_cast<long long>(k) * 3 + c) * p.H + (py * p.patch + ky)) * p.W + x);
+    *reinterpret_cast<uint32_t*>(p.cols + (row0 + px) * p.ldc + c * pp + ky * p.patch + kx) =
+        pack_bf16((v.x - p.mean[c]) * p.istd[c], (v.y - p.mean[c]) * p.istd[c]);
+  }
+  const int padw = p.ldc - 3 * pp;      // even: ldc % 8 == 0 and 3 * patch^2 is even
+  for (int e = threadIdx.x; e < wp * (padw / 2); e += blockDim.x) {
+    const int px = e / (padw / 2), q = e - px * (padw / 2);
+    *reinterpret_cast<uint32_t*>(p.cols + (row0 + px) * p.ldc + 3 * pp + 2 * q) = 0u;
   }
 }
 

@@ -4,6 +4,7 @@
 #include <mutex>
 #include <string>
 #include <unordered_map>
+#include <vector>
 
 #include <cudaTypedefs.h>
 
@@ -488,28 +489,34 @@ int ovg_inject_snapshot(float* x, const float* inj, void* slot, float* cam_out, 
 int ovg_depth_im2col(const float* depth, const float* mask, const int* idx, double* scratch, void* cols, int ldc,
                      int B, int S, int Sd, int H, int W, int patch, void* stream) {
   OVG_REQUIRE(depth && mask && idx && scratch && cols, "null operand");
-  OVG_REQUIRE(B > 0 && Sd > 0 && Sd <= S && H % patch == 0 && W % patch == 0, "bad geometry");
-  OVG_REQUIRE(ldc >= 2 * patch * patch, "ldc too small");
+  OVG_REQUIRE(B > 0 && Sd > 0 && Sd <= S && H % patch == 0 && W % patch == 0 && patch % 2 == 0, "bad geometry");
+  OVG_REQUIRE(ldc >= 2 * patch * patch && ldc % 2 == 0, "ldc too small / odd");
+  OVG_REQUIRE((reinterpret_cast<uintptr_t>(depth) & 7) == 0 && (reinterpret_cast<uintptr_t>(mask) & 7) == 0 &&
+                  (reinterpret_cast<uintptr_t>(cols) & 3) == 0, "depth / mask must be 8-byte aligned");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   ovg::DepthParams p{depth, mask, idx, scratch, reinterpret_cast<__nv_bfloat16*>(cols), ldc, B, S, Sd, H, W, patch};
   ovg::depth_stats_kernel<<<dim3(ovg::DEPTH_NCHUNK, B), 256, 0, st>>>(p);
   int rc = post_launch("ovg_depth_im2col(stats)");
   if (rc) return rc;
-  const int rows = B * Sd * (H / patch) * (W / patch);
-  ovg::depth_im2col_kernel<<<rows, 224, 0, st>>>(p);
+  ovg::depth_scale_kernel<<<B, 256, 0, st>>>(p);
+  rc = post_launch("ovg_depth_im2col(scale)");
+  if (rc) return rc;
+  ovg::depth_im2col_kernel<<<B * Sd * (H / patch), 256, 0, st>>>(p);
   return post_launch("ovg_depth_im2col");
 }
 
 int ovg_image_im2col(const float* images, const float* mean3, const float* std3, void* cols, int ldc, int K, int H, int W,
                      int patch, void* stream) {
   OVG_REQUIRE(images && mean3 && std3 && cols, "null operand");
-  OVG_REQUIRE(K > 0 && H % patch == 0 && W % patch == 0 && ldc >= 3 * patch * patch && ldc % 8 == 0, "bad geometry");
+  OVG_REQUIRE(K > 0 && H % patch == 0 && W % patch == 0 && patch % 2 == 0 && ldc >= 3 * patch * patch && ldc % 8 == 0,
+              "bad geometry");
+  OVG_REQUIRE((reinterpret_cast<uintptr_t>(images) & 7) == 0, "images must be 8-byte aligned");
   ovg::ImageColParams p{images, reinterpret_cast<__nv_bfloat16*>(cols), ldc, K, H, W, patch, {}, {}};
   for (int c = 0; c < 3; ++c) {
     p.mean[c] = mean3[c];
     p.istd[c] = 1.0f / std3[c];
   }
-  ovg::image_im2col_kernel<<<K * (H / patch) * (W / patch), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  ovg::image_im2col_kernel<<<K * (H / patch), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
   return post_launch("ovg_image_im2col");
 }
 
@@ -608,3 +615,5 @@ int ovg_conf_percentile_mask(const float* conf, long long n, float percent, floa
 }
 
 }  // extern "C"
+
+#include "runtime.inc"

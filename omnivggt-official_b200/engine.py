@@ -1,10 +1,12 @@
-"""Hot-path engine: weight repacking into kernel layouts, workspace management and the launch sequence of the
-aggregator (reference models/omnivggt_aggregator.py:130-305) and the DPT heads (reference
-heads/dpt_head.py:128-304) on libovg.  All arithmetic happens in the CUDA library; this file only sequences
-kernels on the current stream and owns device buffers."""
+"""Hot-path engine: weight repacking into kernel layouts and device-buffer ownership for the libovg RUNTIME handles.
+The launch sequences of the aggregator (reference models/omnivggt_aggregator.py:130-305), of the frozen DINOv2 patchifier
+(layers/vision_transformer.py:214-271) and of the DPT heads (heads/dpt_head.py:128-304) live in C++
+(csrc/runtime.inc: ovg_aggregator_forward / ovg_dino_forward / ovg_dpt_forward); this file packs the checkpoint tensors
+once, describes them to the library (ovg_*_desc), owns workspaces / outputs and makes one C call per component."""
 from __future__ import annotations
 
-from dataclasses import dataclass
+import ctypes as C
+from dataclasses import dataclass, fields
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -49,6 +51,20 @@ def pack_block(bp) -> BlockPack:
                      _bf(bp.mlp.fc2.weight), _f32(bp.mlp.fc2.bias), _f32(bp.ls2.gamma))
 
 
+def block_struct(bp: BlockPack) -> L.BlockWeights:
+    w = L.BlockWeights()
+    for f in fields(bp):
+        setattr(w, f.name, L.ptr(getattr(bp, f.name)))
+    return w
+
+
+def _block_array(packs: Sequence[BlockPack]):
+    arr = (L.BlockWeights * len(packs))()
+    for i, bp in enumerate(packs):
+        arr[i] = block_struct(bp)
+    return arr
+
+
 class DPTPack:
     """Kernel-layout weights of one DPT head.  The shared LayerNorm affine (heads/dpt_head.py:66,:227) is folded
     into the 1x1 projections: W (g*xhat + b) + c = (W*g) xhat + (W b + c)."""
@@ -84,6 +100,26 @@ class DPTPack:
         self.w2, self.b2 = _f32(s.output_conv2["2"].weight.detach().flatten(1)), _f32(s.output_conv2["2"].bias)
         self.outc = self.w2.shape[0]
 
+    def desc(self, C2: int, patch: int) -> L.DptDesc:
+        d = L.DptDesc()
+        d.C2, d.feat, d.patch, d.outc = C2, self.feat, patch, self.outc
+        for l in range(4):
+            d.oc[l] = self.oc[l]
+            d.proj_w[l], d.proj_b[l] = L.ptr(self.proj_w[l]), L.ptr(self.proj_b[l])
+            d.rn_w[l] = L.ptr(self.rn_w[l])
+            fu = self.fus[l]
+            for k, u in enumerate(("resConfUnit1", "resConfUnit2")):
+                dst = d.fus[l].rcu1 if k == 0 else d.fus[l].rcu2
+                for j in range(4):
+                    dst[j] = L.ptr(fu[u][j]) if u in fu else None
+            d.fus[l].oc_w, d.fus[l].oc_b = L.ptr(fu["oc_w"]), L.ptr(fu["oc_b"])
+        for l in range(2):
+            d.up_w[l], d.up_b[l] = L.ptr(self.up_w[l]), L.ptr(self.up_b[l])
+        d.down_w, d.down_b = L.ptr(self.down_w), L.ptr(self.down_b)
+        d.oc1_w, d.oc1_b, d.oc2_w, d.oc2_b = L.ptr(self.oc1_w), L.ptr(self.oc1_b), L.ptr(self.oc2_w), L.ptr(self.oc2_b)
+        d.w2, d.b2 = L.ptr(self.w2), L.ptr(self.b2)
+        return d
+
 
 class Workspace:
     """Named device buffers, reused across calls (stable addresses keep the TMA descriptor cache hot)."""
@@ -109,10 +145,6 @@ class Workspace:
         return v
 
 
-def _taps(w: int) -> List[int]:
-    return [(ky - 1) * (w + 2) + (kx - 1) for ky in range(3) for kx in range(3)]
-
-
 class Engine:
     def __init__(self, model):
         self.m = model
@@ -125,6 +157,8 @@ class Engine:
         if self.C % 64:
             raise ValueError(f"embed_dim {self.C}: the attention / QKV kernels are built for head_dim 64 (embed_dim % 64 == 0)")
         self.patch = model.patch_size
+        lib = L.lib()
+        # ---- packed weights (kept alive here: the runtime handles only hold their device pointers)
         self.frame = [pack_block(b) for b in ag.frame_blocks]
         self.glob = [pack_block(b) for b in ag.global_blocks]
         self.cam_tok = _f32(ag.camera_token.reshape(2, self.C))
@@ -135,6 +169,19 @@ class Engine:
         self.depth_b = _f32(ag.depth_patch_embed.proj.bias)
         self.ones_c = torch.ones(self.C, device=self.device, dtype=F32)
         self.inj_pack = pack_injection(ag)
+        self.keep = tuple(model.dpt_layers)
+        self._handles = []
+        d = L.AggregatorDesc()
+        d.C, d.registers, d.depth, d.patch = self.C, self.R, self.depth, self.patch
+        self._fb, self._gb = _block_array(self.frame), _block_array(self.glob)
+        d.frame_blocks, d.global_blocks = self._fb, self._gb
+        d.cam_tok, d.reg_tok, d.placeholder = L.ptr(self.cam_tok), L.ptr(self.reg_tok), L.ptr(self.placeholder)
+        d.depth_w, d.depth_b, d.ones_c = L.ptr(self.depth_w), L.ptr(self.depth_b), L.ptr(self.ones_c)
+        for i in range(4):
+            d.keep_layers[i] = self.keep[i]
+        self.h_agg = C.c_void_p()
+        L.check(lib.ovg_aggregator_create(C.byref(d), C.byref(self.h_agg)))
+        self._handles.append((lib.ovg_aggregator_destroy, self.h_agg))
         # frozen DINOv2 patchifier on the same kernels: reference
         # layers/vision_transformer.py:214-271 -- blocks without RoPE / q-k norm, LayerNorm eps 1e-6, LayerScale gammas
         self.dino = None
@@ -148,15 +195,36 @@ class Engine:
             wpad = torch.zeros(w.shape[0], kpad, device=self.device, dtype=BF16)
             wpad[:, :w.shape[1]] = w.to(BF16)
             self.dino = dict(blocks=[pack_block(b) for b in pe.blocks], w=wpad, b=_f32(pe.patch_embed.proj.bias),
-                             norm_w=_f32(pe.norm.weight), norm_b=_f32(pe.norm.bias), heads=pe.heads,
-                             nreg=pe.register_tokens.shape[1], kpad=kpad)
+                             norm_w=_f32(pe.norm.weight), norm_b=_f32(pe.norm.bias), nreg=pe.register_tokens.shape[1], kpad=kpad)
+            dd = L.DinoDesc()
+            dd.C, dd.registers, dd.depth, dd.patch, dd.kpad = self.C, self.dino["nreg"], len(pe.blocks), self.patch, kpad
+            self._db = _block_array(self.dino["blocks"])
+            dd.blocks = self._db
+            dd.w_patch, dd.b_patch = L.ptr(wpad), L.ptr(self.dino["b"])
+            dd.norm_w, dd.norm_b, dd.ones_c = L.ptr(self.dino["norm_w"]), L.ptr(self.dino["norm_b"]), L.ptr(self.ones_c)
+            self.h_dino = C.c_void_p()
+            L.check(lib.ovg_dino_create(C.byref(dd), C.byref(self.h_dino)))
+            self._handles.append((lib.ovg_dino_destroy, self.h_dino))
         self.dpt_packs = {name: DPTPack(getattr(model, name)) for name in ("depth_head", "point_head")
-                    if getattr(model, name, None) is not None}
+                          if getattr(model, name, None) is not None}
+        self.h_dpt = {}
+        for name, pk in self.dpt_packs.items():
+            h = C.c_void_p()
+            desc = pk.desc(2 * self.C, self.patch)
+            L.check(lib.ovg_dpt_create(C.byref(desc), C.byref(h)))
+            self.h_dpt[name] = h
+            self._handles.append((lib.ovg_dpt_destroy, h))
         self.ws = Workspace(self.device)
-        self.attn_events = None      # bench.py sets this to a list to time the global-attention launches
         self._idx_cache: Dict[tuple, torch.Tensor] = {}   # small device index tensors (no per-call H2D copies)
         self._rope: Dict[int, Tuple[torch.Tensor, torch.Tensor]] = {}
         self._tables: Dict[tuple, torch.Tensor] = {}
+
+    def __del__(self):
+        for destroy, h in getattr(self, "_handles", []):
+            try:
+                destroy(h)
+            except Exception:
+                pass
 
     # ------------------------------------------------------------------------------------------ helpers
     def rope(self, maxpos: int):
@@ -172,16 +240,16 @@ class Engine:
             self._idx_cache[key] = t
         return t
 
-    def table(self, C: int, h: int, w: int, aspect: float) -> torch.Tensor:
-        key = (C, h, w, round(aspect, 9))
+    def table(self, C_: int, h: int, w: int, aspect: float) -> torch.Tensor:
+        key = (C_, h, w, round(aspect, 9))
         if key not in self._tables:
-            self._tables[key] = uv_posembed_table(C, h, w, aspect, self.device)
+            self._tables[key] = uv_posembed_table(C_, h, w, aspect, self.device)
         return self._tables[key]
 
-    def table_xy(self, C: int, h: int, w: int, aspect: float):
-        key = ("xy", C, h, w, round(aspect, 9))
+    def table_xy(self, C_: int, h: int, w: int, aspect: float):
+        key = ("xy", C_, h, w, round(aspect, 9))
         if key not in self._tables:
-            self._tables[key] = uv_posembed_separable(C, h, w, aspect, self.device)
+            self._tables[key] = uv_posembed_separable(C_, h, w, aspect, self.device)
         return self._tables[key]
 
     def warm_tables(self, H: int, W: int):
@@ -193,200 +261,61 @@ class Engine:
                 self.table(oc, hp, wp, W / H)
             self.table_xy(pk.feat // 2, hp * self.patch, wp * self.patch, W / H)
 
+    def _workspace(self, name: str, nbytes: int) -> torch.Tensor:
+        if nbytes < 0:
+            raise L.OvgError("libovg: workspace size query failed")
+        return self.ws.get(name, (nbytes,), torch.uint8)
+
     # ------------------------------------------------------------------------------------------ DINOv2 patchifier
     def dino_patchify(self, images: torch.Tensor, pos_embed: torch.Tensor, mean, std) -> torch.Tensor:
         """images fp32 [K,3,H,W] in [0,1] -> x_norm_patchtokens fp32 [K,P,C] (reference
         layers/vision_transformer.py:214-271).  pos_embed: fp32 [1, 1+P, C], already interpolated to this grid."""
-        d, ws, C = self.dino, self.ws, self.C
+        lib, d = L.lib(), self.dino
         K, _, H, W = images.shape
-        hp, wp = H // self.patch, W // self.patch
-        P, nreg = hp * wp, d["nreg"]
-        Td = 1 + nreg + P
+        P = (H // self.patch) * (W // self.patch)
         pe = self.m.aggregator.patch_embed
-        # token assembly: [cls + pos0, registers, pos_patches] broadcast over frames; the patch-embedding GEMM adds on top
-        base = torch.cat([pe.cls_token.float() + pos_embed[:, :1], pe.register_tokens.float(), pos_embed[:, 1:]], 1)
-        x = ws.get("dino_x", (K, Td, C), F32)
-        x.copy_(base.expand(K, -1, -1))
-        cols = ws.get("dino_cols", (K * P, d["kpad"]))
-        ops.image_im2col(images.contiguous(), mean, std, cols, K, H, W, self.patch)
-        rows = self.cached(("dino_rows", K, Td, P), lambda: (
-            (torch.arange(K) * Td)[:, None] + (1 + nreg) + torch.arange(P)[None]).reshape(-1).to(torch.int32))
-        x2 = x.view(K * Td, C)
-        ops.linear_resid(cols, d["w"], d["b"], self.ones_c, x2, row_index=rows)
-        for bp in d["blocks"]:
-            self.block(bp, x2, K, Td, Td, 1, None, eps=1e-6)
-        out = ws.get("dino_out", (K, P, C), F32)
-        ops.layernorm(x2, out.view(K * P, C), d["norm_w"], d["norm_b"], 1e-6, rows=K * P, grp_out=P, grp_in=Td, grp_off=1 + nreg)
+        # [cls + pos0, registers, pos_patches]: the same for every frame; the patch-embedding GEMM adds on top
+        base = torch.cat([pe.cls_token.float() + pos_embed[:, :1], pe.register_tokens.float(), pos_embed[:, 1:]], 1).contiguous()
+        wsb = self._workspace("dino_ws", lib.ovg_dino_workspace_bytes(self.h_dino, K, H, W))
+        out = self.ws.get("dino_out", (K, P, self.C), F32)
+        m3 = (C.c_float * 3)(*[float(v) for v in mean])
+        s3 = (C.c_float * 3)(*[float(v) for v in std])
+        img = images.contiguous()
+        L.check(lib.ovg_dino_forward(self.h_dino, img.data_ptr(), base.data_ptr(), C.cast(m3, C.c_void_p), C.cast(s3, C.c_void_p),
+                                     K, H, W, wsb.data_ptr(), wsb.numel(), out.data_ptr(), L.stream()))
         return out
 
     # ------------------------------------------------------------------------------------------ aggregator
-    def block(self, bp: BlockPack, x2: torch.Tensor, batch: int, ntok: int, T: int, wp: int, rope, eps: float = 1e-5):
-        """x += g1 * proj(attn(LN1 x)); x += g2 * fc2(gelu(fc1(LN2 x)))   (reference layers/block.py:81-107)."""
-        M, C = x2.shape
-        ws = self.ws
-        xn = ws.get("xn", (M, C))
-        q = ws.get("q", (batch, self.heads, ntok, 64))
-        k = ws.get("k", (batch, self.heads, ntok, 64))
-        v = ws.get("v", (batch, self.heads, ntok, 64))
-        o = ws.get("o", (M, C))
-        h = ws.get("h", (M, 4 * C))
-        ops.layernorm(x2, xn, bp.ln1_w, bp.ln1_b, eps)
-        ops.qkv_proj(xn, bp.w_qkv, bp.b_qkv, bp.qn_w, bp.qn_b, bp.kn_w, bp.kn_b, q, k, v, ntok=ntok, T=T,
-                     nspecial=self.R + 1, wp=wp, rope_cos=rope[0] if rope else None, rope_sin=rope[1] if rope else None)
-        if self.attn_events is not None and ntok > T:
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            ops.attention(q, k, v, o, batch, self.heads, ntok)
-            e1.record()
-            self.attn_events.append((e0, e1, batch, ntok))
-        else:
-            ops.attention(q, k, v, o, batch, self.heads, ntok)
-        ops.linear_resid(o, bp.w_proj, bp.b_proj, bp.g1, x2)
-        ops.layernorm(x2, xn, bp.ln2_w, bp.ln2_b, eps)
-        ops.linear_bf16(xn, bp.w_fc1, bp.b_fc1, act=L.ACT_GELU, out=h)
-        ops.linear_resid(h, bp.w_fc2, bp.b_fc2, bp.g2, x2)
-
     def aggregate(self, patch_tokens: torch.Tensor, inj: torch.Tensor, depth: Optional[torch.Tensor],
                   mask: Optional[torch.Tensor], depth_idx: List[int], B: int, S: int, H: int, W: int,
                   keep: Sequence[int]):
         """patch_tokens fp32 [K,P,C]; inj fp32 [depth+1,K,C].  Returns ({layer: bf16 slot [K,T,2C]}, cam fp32 [K,2C])."""
-        C, R = self.C, self.R
+        lib = L.lib()
+        Cc, R = self.C, self.R
         K = B * S
         hp, wp = H // self.patch, W // self.patch
-        P = hp * wp
-        T = P + R + 1
-        ws = self.ws
-        x = ws.get("x", (K, T, C), F32)
-        def _has_depth():
-            h = torch.zeros(B, S, dtype=torch.int32)
-            if len(depth_idx):
-                h[:, depth_idx] = 1
-            return h.reshape(K)
-        has_depth = self.cached(("has_depth", B, S, tuple(depth_idx)), _has_depth)
-        ops.assemble_tokens(x, patch_tokens, self.cam_tok, self.reg_tok, inj[0], self.placeholder, has_depth, K, S, T, R, C)
-        x2 = x.view(K * T, C)
-        if len(depth_idx):
-            Sd = len(depth_idx)
-            idx = self.cached(("depth_idx", tuple(depth_idx)), lambda: torch.tensor(depth_idx, dtype=torch.int32))
-            kk = 2 * self.patch * self.patch
-            cols = ws.get("depth_cols", (B * Sd * P, kk))
-            scratch = ws.get("depth_scratch", (B * 128 * 2,), torch.float64)
-            d32 = depth.reshape(B, S, H, W).to(F32).contiguous()
-            m32 = mask.reshape(B, S, H, W).to(F32).contiguous()
-            ops.depth_im2col(d32, m32, idx, scratch, cols, B, S, Sd, H, W, self.patch)
-            rows = self.cached(("depth_rows", B, S, T, P, tuple(depth_idx)), lambda: (
-                ((torch.arange(B)[:, None] * S + torch.tensor(depth_idx)[None]) * T)[:, :, None] + (R + 1) +
-                torch.arange(P)[None, None]).reshape(-1).to(torch.int32))
-            ops.linear_resid(cols, self.depth_w, self.depth_b, self.ones_c, x2, row_index=rows)
+        T = hp * wp + R + 1
         if max(hp, wp) + 1 > 64:
             raise ValueError(f"{H}x{W} input: the fused RoPE epilogue holds 64 positions per axis (at most 882 px per side)")
-        rope = self.rope(max(hp, wp) + 1)
-        slots: Dict[int, torch.Tensor] = {}
-        cam_out = ws.get("cam_out", (K, 2 * C), F32)
-        last = self.depth - 1
-        for i in range(self.depth):
-            self.block(self.frame[i], x2, K, T, T, wp, rope)
-            kept = i in keep
-            slot = ws.get(f"slot{i}", (K * T, 2 * C)) if kept else None
-            ops.inject_snapshot(x2, inj[i + 1], slot, cam_out if i == last else None, K, T, C, 0)
-            self.block(self.glob[i], x2, B, S * T, T, wp, rope)
-            if kept or i == last:
-                ops.inject_snapshot(x2, None, slot, cam_out if i == last else None, K, T, C, C)
-            if kept:
-                slots[i] = slot.view(K, T, 2 * C)
-        return slots, cam_out
+        assert tuple(keep) == self.keep or set(keep) == set(self.keep), "kept layers are fixed when the engine is built"
+        cos, sin = self.rope(max(hp, wp) + 1)
+        Sd = len(depth_idx)
+        idx = d32 = m32 = None
+        if Sd:
+            idx = self.cached(("depth_idx", tuple(depth_idx)), lambda: torch.tensor(depth_idx, dtype=torch.int32))
+            d32 = depth.reshape(B, S, H, W).to(F32).contiguous()
+            m32 = mask.reshape(B, S, H, W).to(F32).contiguous()
+        wsb = self._workspace("agg_ws", lib.ovg_aggregator_workspace_bytes(self.h_agg, B, S, H, W, Sd))
+        slot_t = [self.ws.get(f"slot{i}", (K, T, 2 * Cc)) for i in self.keep]
+        slot_p = (C.c_void_p * 4)(*[t.data_ptr() for t in slot_t])
+        cam_out = self.ws.get("cam_out", (K, 2 * Cc), F32)
+        pt, ij = patch_tokens.contiguous(), inj.contiguous()
+        L.check(lib.ovg_aggregator_forward(self.h_agg, pt.data_ptr(), ij.data_ptr(), L.ptr(d32), L.ptr(m32), L.ptr(idx), Sd,
+                                           cos.data_ptr(), sin.data_ptr(), cos.shape[0], B, S, H, W, wsb.data_ptr(), wsb.numel(),
+                                           slot_p, cam_out.data_ptr(), L.stream()))
+        return dict(zip(self.keep, slot_t)), cam_out
 
     # ------------------------------------------------------------------------------------------ DPT head
-    def conv3x3(self, src, w, bias, dst, F_, h, wd, *, act=L.ACT_NONE, skip1=None, skip2=None):
-        cin = src.shape[-1]
-        ops.gemm(src.reshape(-1, cin), w, taps=_taps(wd), epi=L.EPI_BF16, bias=bias, act=act, out=dst, ldo=dst.shape[-1],
-                 skip1=skip1, skip2=skip2, rowmap=L.ROWS_PAD, gh=h, gw=wd)
-
-    def dpt_chunk(self, pk: DPTPack, slots: List[torch.Tensor], f0: int, Fc: int, H: int, W: int, head_act: int,
-                  preds: torch.Tensor, conf: torch.Tensor, ns: str = ""):
-        """One frame chunk of one head (reference heads/dpt_head.py:185-304).  slots: 4 x bf16 [K,T,2C].
-        ``ns`` namespaces the workspace buffers so that the two heads can run concurrently on different streams."""
-        R = self.R
-        _ws = self.ws
-
-        class _NS:        # thin view of the workspace with prefixed buffer names
-            @staticmethod
-            def get(name, shape, dtype=BF16, zero=False):
-                return _ws.get(ns + name, shape, dtype, zero)
-        ws = _NS
-        hp, wp = H // self.patch, W // self.patch
-        P, T, C2 = hp * wp, hp * wp + R + 1, 2 * self.C
-        aspect = W / H
-        f = pk.feat
-        sizes = [(4 * hp, 4 * wp), (2 * hp, 2 * wp), (hp, wp), ((hp - 1) // 2 + 1, (wp - 1) // 2 + 1)]
-        lr = []
-        for lvl in range(4):
-            oc = pk.oc[lvl]
-            xhat = ws.get("dpt_xhat", (Fc * P, C2))
-            ops.layernorm(slots[lvl][f0:f0 + Fc].reshape(Fc * T, C2), xhat, None, None, 1e-5, rows=Fc * P,
-                          grp_out=P, grp_in=T, grp_off=R + 1)
-            tab = self.table(oc, hp, wp, aspect)
-            lh, lw = sizes[lvl]
-            feat = ws.get(f"dpt_feat{lvl}", (Fc, lh + 2, lw + 2, oc))
-            if lvl == 2:
-                feat.zero_()
-                ops.gemm(xhat, pk.proj_w[lvl], epi=L.EPI_BF16, bias=pk.proj_b[lvl], table=tab, table_rows=P, out=feat,
-                         ldo=oc, rowmap=L.ROWS_DENSE2PAD, gh=hp, gw=wp)
-            else:
-                dense = ws.get("dpt_dense", (Fc * P, oc))
-                ops.gemm(xhat, pk.proj_w[lvl], epi=L.EPI_BF16, bias=pk.proj_b[lvl], table=tab, table_rows=P, out=dense,
-                         ldo=oc)
-                feat.zero_()
-                if lvl < 2:
-                    ps = 4 if lvl == 0 else 2
-                    ops.gemm(dense, pk.up_w[lvl], epi=L.EPI_BF16, bias=pk.up_b[lvl], out=feat, ldo=oc,
-                             rowmap=L.ROWS_PIXSHUF, gh=hp, gw=wp, ps=ps, cout=oc)
-                else:
-                    cols = ws.get("dpt_cols", (Fc * lh * lw, 9 * oc))
-                    ops.im2col3x3s2(dense, cols, Fc, hp, wp, oc)
-                    ops.gemm(cols, pk.down_w, epi=L.EPI_BF16, bias=pk.down_b, out=feat, ldo=oc,
-                             rowmap=L.ROWS_DENSE2PAD, gh=lh, gw=lw)
-            # layerN_rn (no bias); only relu(l_rn) is ever consumed (in-place ReLU quirk, dpt_head.py:315,:389)
-            l = ws.get(f"dpt_lr{lvl}", (Fc, lh + 2, lw + 2, f))
-            self.conv3x3(feat, pk.rn_w[lvl], None, l, Fc, lh, lw, act=L.ACT_RELU)
-            lr.append(l)
-        # fusion: refinenet4 -> 3 -> 2 -> 1
-        X = None
-        for lvl in (3, 2, 1, 0):
-            fu = pk.fus[lvl]
-            lh, lw = sizes[lvl]
-            shp = (Fc, lh + 2, lw + 2, f)
-            if X is None:
-                U = lr[lvl]
-            else:
-                c1w, c1b, c2w, c2b = fu["resConfUnit1"]
-                t1 = ws.get("dpt_t", shp)
-                self.conv3x3(lr[lvl], c1w, c1b, t1, Fc, lh, lw, act=L.ACT_RELU)
-                U = ws.get("dpt_u", shp)
-                self.conv3x3(t1, c2w, c2b, U, Fc, lh, lw, act=L.ACT_RELU, skip1=lr[lvl], skip2=X)
-            c1w, c1b, c2w, c2b = fu["resConfUnit2"]
-            t2 = ws.get("dpt_t", shp)
-            self.conv3x3(U, c1w, c1b, t2, Fc, lh, lw, act=L.ACT_RELU)
-            V = ws.get("dpt_v", shp)
-            self.conv3x3(t2, c2w, c2b, V, Fc, lh, lw, skip1=U)
-            # out_conv (1x1) commutes with the bilinear resize; apply it at the low resolution
-            Wv = ws.get("dpt_w", shp)
-            ops.gemm(V.reshape(-1, f), fu["oc_w"], epi=L.EPI_BF16, bias=fu["oc_b"], out=Wv, ldo=f, rowmap=L.ROWS_PAD,
-                     gh=lh, gw=lw)
-            th, tw = sizes[lvl - 1] if lvl > 0 else (2 * lh, 2 * lw)
-            X = ws.get(f"dpt_x{lvl}", (Fc, th + 2, tw + 2, f))
-            ops.upsample_bilinear(Wv, X, None, None, Fc, lh, lw, th, tw, f)
-        th, tw = 2 * sizes[0][0], 2 * sizes[0][1]
-        o1 = ws.get("dpt_o1", (Fc, th + 2, tw + 2, f // 2))
-        self.conv3x3(X, pk.oc1_w, pk.oc1_b, o1, Fc, th, tw)
-        Hh, Ww = hp * self.patch, wp * self.patch
-        up = ws.get("dpt_up", (Fc, Hh + 2, Ww + 2, f // 2))
-        tx, ty = self.table_xy(f // 2, Hh, Ww, aspect)
-        ops.upsample_bilinear(o1, up, tx, ty, Fc, th, tw, Hh, Ww, f // 2)
-        ops.gemm(up.reshape(-1, f // 2), pk.oc2_w, taps=_taps(Ww), epi=L.EPI_HEADTAIL, bias=pk.oc2_b, w2=pk.w2, b2=pk.b2,
-                 outc=pk.outc, head_act=head_act, preds=preds[f0:f0 + Fc], conf=conf[f0:f0 + Fc], rowmap=L.ROWS_PAD,
-                 gh=Hh, gw=Ww)
-
     def dpt_alloc(self, name: str, K: int, H: int, W: int):
         pk = self.dpt_packs[name]
         return (torch.empty(K, H, W, pk.outc - 1, device=self.device, dtype=F32),
@@ -394,9 +323,20 @@ class Engine:
 
     def dpt(self, name: str, slots: Dict[int, torch.Tensor], layers: Sequence[int], K: int, H: int, W: int,
             head_act: int, chunk: int = 8, out=None):
-        pk = self.dpt_packs[name]
+        """One DPT head over all K frames in chunks of 8 (reference heads/dpt_head.py:153-183: results are chunk independent).
+        Every head has its own workspace, so the two heads may run concurrently on different streams."""
+        lib, pk = L.lib(), self.dpt_packs[name]
         preds, conf = out if out is not None else self.dpt_alloc(name, K, H, W)
-        sl = [slots[i] for i in layers]
+        hp, wp = H // self.patch, W // self.patch
+        T = hp * wp + self.R + 1
+        slot_p = (C.c_void_p * 4)(*[slots[i].data_ptr() for i in layers])
+        tabs = [self.table(oc, hp, wp, W / H) for oc in pk.oc]
+        tab_p = (C.c_void_p * 4)(*[t.data_ptr() for t in tabs])
+        tx, ty = self.table_xy(pk.feat // 2, hp * self.patch, wp * self.patch, W / H)
+        fc_max = min(chunk, K)
+        wsb = self._workspace(name + ".ws", lib.ovg_dpt_workspace_bytes(self.h_dpt[name], fc_max, H, W))
         for f0 in range(0, K, chunk):
-            self.dpt_chunk(pk, sl, f0, min(chunk, K - f0), H, W, head_act, preds, conf, ns=name + ".")
+            L.check(lib.ovg_dpt_forward(self.h_dpt[name], slot_p, T, self.R + 1, f0, min(chunk, K - f0), H, W, tab_p,
+                                        tx.data_ptr(), ty.data_ptr(), head_act, preds.data_ptr(), conf.data_ptr(),
+                                        wsb.data_ptr(), wsb.numel(), L.stream()))
         return preds, conf

@@ -1,6 +1,9 @@
-"""Host-logic dry run (CPU): the engine's full launch sequence (aggregator + both DPT heads, every aux / chunking / shape
-path) executed with the C library replaced by a recorder.  Catches Python-level sequencing, shape and argument errors
-without a GPU; numerical correctness is covered by the -m gpu tests."""
+"""Host-logic dry run (CPU): the boundary module + engine against a recorder in place of the C library.  The launch
+SEQUENCES live in C++ (csrc/runtime.inc) and are covered by the -m gpu goldens; what is checked here is the Python side of the
+runtime API: one handle per component, one forward call per component and DPT chunk, descriptors filled from the packed
+weights, shapes of the returned dict -- for every aux / chunking / shape path."""
+import ctypes
+
 import pytest
 import torch
 
@@ -11,10 +14,14 @@ from test_host_cpu import mini_model
 class _Recorder:
     def __init__(self):
         self.calls = []
+        self.descs = {}
 
     def __getattr__(self, name):
         def fn(*a):
             self.calls.append(name)
+            if name.endswith("_create"):
+                d = a[0]._obj                       # ctypes.byref(desc)
+                self.descs[name] = type(d).from_buffer_copy(d)
             return 0
         return fn
 
@@ -29,8 +36,7 @@ def dry(monkeypatch):
     return rec
 
 
-def test_launch_sequence_dino_backend(dry):
-    """The frozen DINOv2 patchifier on the libovg kernels: 2 blocks -> 2 attention launches + image im2col + embed GEMM."""
+def test_runtime_calls_dino_backend(dry):
     from omnivggt_official_b200.engine import Engine
     m = mini_model("mini_dino").eval()
     m._engine = Engine(m)
@@ -39,12 +45,13 @@ def test_launch_sequence_dino_backend(dry):
     out = m(images=inp["images"])
     assert out["depth"].shape == (1, 2, 42, 70, 1)
     n = dry.calls.count
-    assert n("ovg_image_im2col") == 1 and n("ovg_attention") == 2 * 4 + 2
-    assert n("ovg_layernorm") == 4 * 4 + 2 * 2 + 1 + 2 * 4
+    assert n("ovg_dino_create") == 1 and n("ovg_dino_forward") == 1 and n("ovg_aggregator_forward") == 1
+    d = dry.descs["ovg_dino_create"]
+    assert (d.C, d.registers, d.depth, d.patch, d.kpad) == (128, 4, 2, 14, 592) and d.blocks[1].w_fc2 and not d.blocks[0].qn_w
 
 
 @pytest.mark.parametrize("B,S,H,W,didx,cidx", [(1, 2, 56, 56, [], []), (2, 3, 42, 70, [0, 2], [0, 1]), (1, 9, 28, 28, [4], [0])])
-def test_launch_sequence(dry, B, S, H, W, didx, cidx):
+def test_runtime_calls(dry, B, S, H, W, didx, cidx):
     from omnivggt_official_b200.engine import Engine
     m = mini_model().eval()
     m._engine = Engine(m)
@@ -53,10 +60,11 @@ def test_launch_sequence(dry, B, S, H, W, didx, cidx):
     assert out["depth"].shape == (B, S, H, W, 1) and out["world_points"].shape == (B, S, H, W, 3)
     assert out["depth_conf"].shape == (B, S, H, W) and out["pose_enc"].shape == (B, S, 9)
     n = dry.calls.count
-    depth = 4
-    assert n("ovg_attention") == 2 * depth and n("ovg_assemble_tokens") == 1
-    assert n("ovg_layernorm") == 4 * depth + 2 * 4 * -(-B * S // 8)
-    assert n("ovg_depth_im2col") == (1 if didx else 0)
-    # per block: qkv, proj, fc1, fc2 ; depth scatter GEMM ; per head-chunk: 4 proj + 2 convT + 1 down + 4 rn + 14 rcu/oc + oc1 + tail
-    per_chunk = 4 + 2 + 1 + 4 + (2 + 1) + 3 * (4 + 1) + 1 + 1
-    assert n("ovg_gemm") == 8 * depth + (1 if didx else 0) + 2 * per_chunk * -(-B * S // 8)
+    assert n("ovg_aggregator_create") == 1 and n("ovg_dpt_create") == 2 and n("ovg_dino_create") == 0
+    assert n("ovg_aggregator_forward") == 1 and n("ovg_dpt_forward") == 2 * -(-B * S // 8)      # chunks of 8 frames per head
+    a = dry.descs["ovg_aggregator_create"]
+    assert (a.C, a.registers, a.depth, a.patch) == (128, 4, 4, 14) and list(a.keep_layers) == [0, 1, 2, 3]
+    assert a.frame_blocks[3].qn_w and a.global_blocks[0].w_qkv and a.depth_w and a.ones_c
+    p = dry.descs["ovg_dpt_create"]
+    assert (p.C2, p.feat, p.patch) == (256, 128, 14) and list(p.oc) == [64, 128, 256, 256] and p.outc in (2, 4)
+    assert not p.fus[3].rcu1[0] and p.fus[0].rcu1[0] and p.fus[3].rcu2[3] and p.up_w[1] and p.down_w

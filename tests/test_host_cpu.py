@@ -58,6 +58,25 @@ def test_ctypes_struct_matches_header():
         assert getattr(_lib.GemmArgs, f).offset == int(off), f
 
 
+@pytest.mark.parametrize("cname,pyname", [("ovg_block_weights", "BlockWeights"), ("ovg_aggregator_desc", "AggregatorDesc"),
+                                          ("ovg_dino_desc", "DinoDesc"), ("ovg_dpt_fusion", "DptFusion"), ("ovg_dpt_desc", "DptDesc")])
+def test_runtime_structs_match_header(cname, pyname):
+    from omnivggt_official_b200 import _lib
+    cls = getattr(_lib, pyname)
+    fields = [f[0] for f in cls._fields_]
+    src = f"#include <stdio.h>\n#include <stddef.h>\n#include \"ovg.h\"\nint main(){{printf(\"%zu\\n\", sizeof({cname}));\n"
+    for f in fields:
+        src += f'printf("%zu\\n", offsetof({cname}, {f}));\n'
+    src += "return 0;}\n"
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "t.c"), "w").write(src)
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", os.path.join(d, "t"), os.path.join(d, "t.c")])
+        out = subprocess.check_output([os.path.join(d, "t")]).decode().split()
+    assert int(out[0]) == ctypes.sizeof(cls)
+    for f, off in zip(fields, out[1:]):
+        assert getattr(cls, f).offset == int(off), f
+
+
 @pytest.mark.parametrize("variant", ["mini_conv", "mini_dino"])
 def test_state_dict_schema_equals_reference(variant):
     m = mini_model(variant)

@@ -49,8 +49,8 @@ def test_gemm_bf16_bias_gelu(M, N, K, bn):
     assert rel(out2, a.float() @ w.float().t()) < 6e-3
 
 
-@pytest.mark.parametrize("M,N,K", [(5000, 1024, 128), (10992, 1024, 256)])
-def test_gemm_resid_split_tail(M, N, K):
+@pytest.mark.parametrize("M,N,K,bn", [(5000, 1024, 128, 512), (10992, 1024, 256, 512)])
+def test_gemm_resid_split_tail(M, N, K, bn):
     """Residual epilogue (bulk reduce-add) over a tile count whose last wave is split into half tiles."""
     ops = _ops()
     a = randn(M, K, seed=1, dtype=BF16)
@@ -58,7 +58,7 @@ def test_gemm_resid_split_tail(M, N, K):
     bias, gamma = randn(N, seed=3), randn(N, seed=4)
     x0 = randn(M, N, seed=5)
     x = x0.clone()
-    ops.linear_resid(a, w, bias, gamma, x, block_n=512)
+    ops.linear_resid(a, w, bias, gamma, x, block_n=bn)
     ref = x0 + gamma * (a.float() @ w.float().t() + bias)
     assert rel(x, ref) < 1e-5
 
@@ -284,7 +284,7 @@ def test_depth_im2col_matches_reference_normalisation():
     mask[1] = 0          # scene without valid pixels -> zeros (omnivggt_aggregator.py:121-122)
     Sd, hp, wp = 3, H // patch, W // patch
     cols = torch.zeros(B * Sd * hp * wp, 2 * patch * patch, device="cuda", dtype=BF16)
-    scratch = torch.zeros(B * 128 * 2, device="cuda", dtype=torch.float64)
+    scratch = torch.zeros(_ops().L.DEPTH_SCRATCH_DOUBLES(B), device="cuda", dtype=torch.float64)
     ops.depth_im2col(depth, mask, idx, scratch, cols, B, S, Sd, H, W, patch)
     d, m = depth[:, idx.long()], mask[:, idx.long()]
     norm = torch.zeros_like(d)

@@ -68,7 +68,7 @@ slot5 = torch.empty(K5 * T, 2 * C, device=dev, dtype=BF16)
 depth5 = 0.5 + 4 * torch.rand(1, K5, 518, 518, device=dev, generator=g)
 mask5 = (torch.rand(1, K5, 518, 518, device=dev, generator=g) > 0.2).float()
 idx5 = torch.tensor(didx, dtype=torch.int32, device=dev)
-scratch5 = torch.zeros(128 * 2, dtype=torch.float64, device=dev)
+scratch5 = torch.zeros(ops.L.DEPTH_SCRATCH_DOUBLES(1), dtype=torch.float64, device=dev)
 cols5 = torch.empty(len(didx) * P5, 392, device=dev, dtype=BF16)
 img5 = torch.rand(K5, 3, 518, 518, device=dev, generator=g)
 icol5 = torch.empty(K5 * P5, 592, device=dev, dtype=BF16)
@@ -79,7 +79,8 @@ def run():
     if ONLY == "attn":
         ops.attention(q, k, v, o, 1, 16, M)
         return
-    run_blocks()
+    if ONLY != "scatter":
+        run_blocks()
     ops.assemble_tokens(x5, patch5, cam_tok, reg_tok, inj0, placeholder, has_depth, K5, K5, T, 4, C)
     ops.inject_snapshot(x5.view(K5 * T, C), inj0, slot5, None, K5, T, C, 0)
     ops.depth_im2col(depth5, mask5, idx5, scratch5, cols5, 1, K5, len(didx), 518, 518, 14)
