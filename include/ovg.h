@@ -227,6 +227,27 @@ int ovg_dpt_forward(ovg_dpt* h, const void* const* slots, int T, int nspecial, i
                     const float* const* tables, const float* tx, const float* ty, int head_act, float* preds, float* conf,
                     void* workspace, long long workspace_bytes, void* stream);
 
+/* Camera head: iterative pose refinement on the camera tokens; reference heads/camera_head.py:83-154.  The weight-streaming
+ * GEMMs run on the tcgen05 GEMM; AdaLN, the S-token attention (head_dim D / heads) and the 9-wide pose update are small fp32
+ * kernels. */
+typedef struct ovg_camera_desc {
+  int D; int heads; int trunk_depth;                           /* 2*embed_dim (2048), 16, 4 */
+  const ovg_block_weights* trunk;                              /* host array [trunk_depth]; qn_w .. kn_b NULL */
+  const float* token_norm_w; const float* token_norm_b; const float* trunk_norm_w; const float* trunk_norm_b;
+  const float* empty_pose;                                     /* fp32 [9] */
+  const float* embed_w; const float* embed_b;                  /* embed_pose: fp32 [D, 9], [D] */
+  const void* mod_w; const float* mod_b;                       /* poseLN_modulation[1]: bf16 [3D, D], fp32 [3D] */
+  const void* fc1_w; const float* fc1_b;                       /* pose_branch.fc1: bf16 [D/2, D], fp32 [D/2] */
+  const float* fc2_w; const float* fc2_b;                      /* pose_branch.fc2: fp32 [9, D/2], [9] */
+} ovg_camera_desc;
+typedef struct ovg_camera ovg_camera;
+int ovg_camera_create(const ovg_camera_desc* desc, ovg_camera** out);
+void ovg_camera_destroy(ovg_camera* h);
+long long ovg_camera_workspace_bytes(const ovg_camera* h, int K);
+/* cam_tokens fp32 [B*S, D]; out fp32 [iters, B*S, 9]: the activated pose encoding after each iteration. */
+int ovg_camera_forward(ovg_camera* h, const float* cam_tokens, int B, int S, int iters, float* out, void* workspace,
+                       long long workspace_bytes, void* stream);
+
 /* Timing hook for bench.py: when enabled, every global-attention launch of ovg_aggregator_forward is bracketed by CUDA events
  * on its stream; after a synchronize, ovg_runtime_attention_times() returns the elapsed ms of the launches since the enable. */
 void ovg_runtime_time_attention(int enable);

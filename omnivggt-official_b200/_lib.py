@@ -74,6 +74,14 @@ class DptDesc(C.Structure):
                 ("w2", _vp), ("b2", _vp)]
 
 
+class CameraDesc(C.Structure):
+    """Mirror of ``ovg_camera_desc``."""
+    _fields_ = [("D", _i), ("heads", _i), ("trunk_depth", _i), ("trunk", C.POINTER(BlockWeights)),
+                ("token_norm_w", _vp), ("token_norm_b", _vp), ("trunk_norm_w", _vp), ("trunk_norm_b", _vp), ("empty_pose", _vp),
+                ("embed_w", _vp), ("embed_b", _vp), ("mod_w", _vp), ("mod_b", _vp), ("fc1_w", _vp), ("fc1_b", _vp),
+                ("fc2_w", _vp), ("fc2_b", _vp)]
+
+
 _pp = C.POINTER(_vp)
 EXPORTS = {
     "ovg_version": (C.c_int, []),
@@ -105,6 +113,10 @@ EXPORTS = {
     "ovg_dpt_destroy": (None, [_vp]),
     "ovg_dpt_workspace_bytes": (_ll, [_vp, _i, _i, _i]),
     "ovg_dpt_forward": (C.c_int, [_vp, _pp, _i, _i, _i, _i, _i, _i, _pp, _vp, _vp, _i, _vp, _vp, _vp, _ll, _vp]),
+    "ovg_camera_create": (C.c_int, [C.POINTER(CameraDesc), _pp]),
+    "ovg_camera_destroy": (None, [_vp]),
+    "ovg_camera_workspace_bytes": (_ll, [_vp, _i]),
+    "ovg_camera_forward": (C.c_int, [_vp, _vp, _i, _i, _i, _vp, _vp, _ll, _vp]),
     "ovg_runtime_time_attention": (None, [_i]),
     "ovg_runtime_attention_times": (C.c_int, [_vp, _i]),
 }

@@ -10,6 +10,7 @@
 
 #include "../../include/ovg.h"
 #include "attn.cuh"
+#include "camera.cuh"
 #include "elem.cuh"
 #include "gemm.cuh"
 #include "post.cuh"

@@ -214,6 +214,29 @@ class Engine:
             L.check(lib.ovg_dpt_create(C.byref(desc), C.byref(h)))
             self.h_dpt[name] = h
             self._handles.append((lib.ovg_dpt_destroy, h))
+        # camera head (reference heads/camera_head.py:83-154) on the same GEMM kernels + small fp32 kernels
+        self.h_cam = None
+        cp = getattr(model, "camera_head", None)
+        if cp is not None and getattr(model, "camera_backend", "ovg") == "ovg":
+            D = cp.token_norm.weight.shape[0]
+            self.cam = dict(trunk=[pack_block(b) for b in cp.trunk], tn_w=_f32(cp.token_norm.weight), tn_b=_f32(cp.token_norm.bias),
+                            rn_w=_f32(cp.trunk_norm.weight), rn_b=_f32(cp.trunk_norm.bias),
+                            empty=_f32(cp.empty_pose_tokens.reshape(9)), ew=_f32(cp.embed_pose.weight), eb=_f32(cp.embed_pose.bias),
+                            mw=_bf(cp.poseLN_modulation["1"].weight), mb=_f32(cp.poseLN_modulation["1"].bias),
+                            f1w=_bf(cp.pose_branch.fc1.weight), f1b=_f32(cp.pose_branch.fc1.bias),
+                            f2w=_f32(cp.pose_branch.fc2.weight), f2b=_f32(cp.pose_branch.fc2.bias), D=D)
+            cd = L.CameraDesc()
+            cd.D, cd.heads, cd.trunk_depth = D, cp.heads, len(cp.trunk)
+            self._cb = _block_array(self.cam["trunk"])
+            cd.trunk = self._cb
+            c = self.cam
+            cd.token_norm_w, cd.token_norm_b, cd.trunk_norm_w, cd.trunk_norm_b = L.ptr(c["tn_w"]), L.ptr(c["tn_b"]), L.ptr(c["rn_w"]), L.ptr(c["rn_b"])
+            cd.empty_pose, cd.embed_w, cd.embed_b = L.ptr(c["empty"]), L.ptr(c["ew"]), L.ptr(c["eb"])
+            cd.mod_w, cd.mod_b, cd.fc1_w, cd.fc1_b = L.ptr(c["mw"]), L.ptr(c["mb"]), L.ptr(c["f1w"]), L.ptr(c["f1b"])
+            cd.fc2_w, cd.fc2_b = L.ptr(c["f2w"]), L.ptr(c["f2b"])
+            self.h_cam = C.c_void_p()
+            L.check(lib.ovg_camera_create(C.byref(cd), C.byref(self.h_cam)))
+            self._handles.append((lib.ovg_camera_destroy, self.h_cam))
         self.ws = Workspace(self.device)
         self._idx_cache: Dict[tuple, torch.Tensor] = {}   # small device index tensors (no per-call H2D copies)
         self._rope: Dict[int, Tuple[torch.Tensor, torch.Tensor]] = {}
@@ -314,6 +337,17 @@ class Engine:
                                            cos.data_ptr(), sin.data_ptr(), cos.shape[0], B, S, H, W, wsb.data_ptr(), wsb.numel(),
                                            slot_p, cam_out.data_ptr(), L.stream()))
         return dict(zip(self.keep, slot_t)), cam_out
+
+    # ------------------------------------------------------------------------------------------ camera head
+    def camera_head(self, cam_tokens: torch.Tensor, B: int, S: int, iters: int = 4) -> List[torch.Tensor]:
+        """cam_tokens fp32 [B*S, 2C] -> list of `iters` activated pose encodings fp32 [B, S, 9] (heads/camera_head.py:83-154)."""
+        lib = L.lib()
+        K = B * S
+        wsb = self._workspace("cam.ws", lib.ovg_camera_workspace_bytes(self.h_cam, K))
+        out = torch.empty(iters, K, 9, device=self.device, dtype=F32)
+        ct = cam_tokens.contiguous()
+        L.check(lib.ovg_camera_forward(self.h_cam, ct.data_ptr(), B, S, iters, out.data_ptr(), wsb.data_ptr(), wsb.numel(), L.stream()))
+        return [out[i].view(B, S, 9) for i in range(iters)]
 
     # ------------------------------------------------------------------------------------------ DPT head
     def dpt_alloc(self, name: str, K: int, H: int, W: int):

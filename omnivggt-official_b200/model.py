@@ -37,14 +37,16 @@ class OmniVGGT(nn.Module, PyTorchModelHubMixin):
                  num_register_tokens: int = 4, dpt_features: int = 256,
                  dpt_out_channels: Sequence[int] = (256, 512, 1024, 1024),
                  dpt_layers: Sequence[int] = (4, 11, 17, 23), camera_heads: int = 16, camera_trunk_depth: int = 4,
-                 dino_backend: str = "ovg", dino_dtype: torch.dtype = torch.bfloat16, camera_dtype: torch.dtype = torch.bfloat16,
+                 dino_backend: str = "ovg", dino_dtype: torch.dtype = torch.bfloat16, camera_backend: str = "ovg",
+                 camera_dtype: torch.dtype = torch.bfloat16,
                  use_cuda_graph: Optional[bool] = None, init_seed: Optional[int] = 0):
         super().__init__()
         self.img_size, self.patch_size, self.embed_dim = img_size, patch_size, embed_dim
         self.dpt_layers = tuple(dpt_layers)
         self.dino_backend = dino_backend   # "ovg": frozen patchifier on the libovg kernels; "torch": library kernels
         self.dino_dtype = dino_dtype
-        self.camera_dtype = camera_dtype     # precision of the camera-head weight matrices (fp32 selectable)
+        self.camera_backend = camera_backend  # "ovg": camera head on the libovg runtime; "torch": library kernels
+        self.camera_dtype = camera_dtype     # camera_backend="torch": precision of the weight matrices (fp32 selectable)
         # replay the ~1000 kernel launches of a forward from a CUDA graph once a shape has been seen twice
         self.use_cuda_graph = (os.environ.get("OVG_CUDA_GRAPH", "1") != "0") if use_cuda_graph is None else use_cuda_graph
         self._graphs = {}
@@ -211,6 +213,11 @@ class OmniVGGT(nn.Module, PyTorchModelHubMixin):
         res["images"] = images
         return res
 
+    def _camera(self, eng, cam_tokens, B, S):
+        if eng.h_cam is not None:
+            return eng.camera_head(cam_tokens, B, S)
+        return TP.camera_head(self.camera_head, cam_tokens.view(B, S, -1), dtype=self.camera_dtype)
+
     def _forward_impl(self, eng, images, extrinsics, intrinsics, depth, mask, depth_idx, cam_idx):
         B, S, Cin, H, W = images.shape
         ag = self.aggregator
@@ -261,14 +268,14 @@ class OmniVGGT(nn.Module, PyTorchModelHubMixin):
             s_cam.wait_event(fork)
             s_pt.wait_event(fork)
             with torch.cuda.stream(s_cam):
-                pose_list = TP.camera_head(self.camera_head, cam_tokens.view(B, S, -1), dtype=self.camera_dtype)
+                pose_list = self._camera(eng, cam_tokens, B, S)
             with torch.cuda.stream(s_pt):
                 eng.dpt("point_head", slots, self.dpt_layers, K, H, W, head_act=1, out=p_out)
             eng.dpt("depth_head", slots, self.dpt_layers, K, H, W, head_act=0, out=d_out)
             main.wait_stream(s_cam)
             main.wait_stream(s_pt)
         else:
-            pose_list = TP.camera_head(self.camera_head, cam_tokens.view(B, S, -1), dtype=self.camera_dtype)
+            pose_list = self._camera(eng, cam_tokens, B, S)
             eng.dpt("depth_head", slots, self.dpt_layers, K, H, W, head_act=0, out=d_out)
             eng.dpt("point_head", slots, self.dpt_layers, K, H, W, head_act=1, out=p_out)
         predictions["pose_enc"] = pose_list[-1]

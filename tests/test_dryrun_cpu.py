@@ -62,6 +62,9 @@ def test_runtime_calls(dry, B, S, H, W, didx, cidx):
     n = dry.calls.count
     assert n("ovg_aggregator_create") == 1 and n("ovg_dpt_create") == 2 and n("ovg_dino_create") == 0
     assert n("ovg_aggregator_forward") == 1 and n("ovg_dpt_forward") == 2 * -(-B * S // 8)      # chunks of 8 frames per head
+    assert n("ovg_camera_create") == 1 and n("ovg_camera_forward") == 1
+    c = dry.descs["ovg_camera_create"]
+    assert (c.D, c.heads, c.trunk_depth) == (256, 2, 2) and c.trunk[1].w_fc2 and not c.trunk[0].qn_w and c.fc2_w and c.mod_w
     a = dry.descs["ovg_aggregator_create"]
     assert (a.C, a.registers, a.depth, a.patch) == (128, 4, 4, 14) and list(a.keep_layers) == [0, 1, 2, 3]
     assert a.frame_blocks[3].qn_w and a.global_blocks[0].w_qkv and a.depth_w and a.ones_c

@@ -59,7 +59,8 @@ def test_ctypes_struct_matches_header():
 
 
 @pytest.mark.parametrize("cname,pyname", [("ovg_block_weights", "BlockWeights"), ("ovg_aggregator_desc", "AggregatorDesc"),
-                                          ("ovg_dino_desc", "DinoDesc"), ("ovg_dpt_fusion", "DptFusion"), ("ovg_dpt_desc", "DptDesc")])
+                                          ("ovg_dino_desc", "DinoDesc"), ("ovg_dpt_fusion", "DptFusion"), ("ovg_dpt_desc", "DptDesc"),
+                                          ("ovg_camera_desc", "CameraDesc")])
 def test_runtime_structs_match_header(cname, pyname):
     from omnivggt_official_b200 import _lib
     cls = getattr(_lib, pyname)
