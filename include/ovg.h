@@ -22,7 +22,7 @@ extern "C" {
 #define OVG_E_NODEVICE (-3)
 
 /* Library / device ------------------------------------------------------------------------------------- */
-int ovg_version(void);               /* ABI version, currently 1 */
+int ovg_version(void);               /* ABI version, currently 2 */
 const char* ovg_last_error(void);    /* thread-local message of the last failing call */
 int ovg_device_check(void);          /* OVG_OK iff the current device is sm_100 (B200); OVG_E_NODEVICE otherwise */
 long long ovg_launch_count(void);    /* kernels launched by this library since load (bench.py "gpu_launches") */
@@ -76,6 +76,11 @@ typedef struct ovg_gemm_args {
   int block_n;
   /* OVG_EPI_QKV switches: q/k LayerNorm(64) and 2-D RoPE (both 1 for aggregator blocks, 0 for DINOv2 blocks) */
   int qk_norm; int rope;
+  /* OVG_EPI_QKV, context parallelism (n_peers > 0): the K / V rows of this rank's tokens go to every listed rank's full-length
+   * buffer [batch*heads, peer_ntok, 64] at token offset peer_tok_off (peer-mapped device memory, plain stores over NVLink);
+   * k_out / v_out are then unused.  The exchange of models/aggregator.py:312-341's single SDPA over all views is thereby
+   * fused into the producing GEMM's epilogue. */
+  void* k_peers[8]; void* v_peers[8]; int n_peers; int peer_ntok; long long peer_tok_off;
 } ovg_gemm_args;
 
 int ovg_gemm(const ovg_gemm_args* args, void* stream);
@@ -84,6 +89,10 @@ int ovg_gemm(const ovg_gemm_args* args, void* stream);
  * log2(e)/sqrt(64).  q,k,v: bf16 [batch, heads, n, 64]; out: bf16 [batch, n, heads*64].
  * Replaces F.scaled_dot_product_attention, layers/attention.py:61-66. */
 int ovg_attention(const void* q, const void* k, const void* v, void* out, int batch, int heads, int n, void* stream);
+/* Same with nq query rows and nkv keys / values per (batch, head): q [batch, heads, nq, 64], k, v [batch, heads, nkv, 64],
+ * out [batch, nq, heads*64] (context parallelism: a rank's own queries against the keys / values of all ranks). */
+int ovg_attention_kv(const void* q, const void* k, const void* v, void* out, int batch, int heads, int nq, int nkv,
+                     void* stream);
 
 /* LayerNorm over the last dim, fp32 or bf16 in -> bf16 (or fp32) out, optional affine, optional row gather
  * (out row m <- in row (m / grp_out) * grp_in + grp_off + m % grp_out; grp_out = 0: identity).
@@ -93,8 +102,8 @@ int ovg_layernorm(const void* in, int in_is_bf16, long long ld_in, void* out, in
 
 /* Token assembly + modality scatter (omnivggt_aggregator.py:155-156,:202-213; aggregator.py:343-366). */
 int ovg_assemble_tokens(float* x, const float* patch, const float* cam_tok, const float* reg_tok, const float* inj0,
-                        const float* placeholder, const int* has_depth, int K, int S, int T, int R, int C,
-                        void* stream);
+                        const float* placeholder, const int* has_depth, int K, int S, int T, int R, int C, int view_base,
+                        void* stream);   /* view_base: index of frame 0 within its scene (0 unless the views are sharded) */
 
 /* Per-layer camera-token injection + bf16 snapshot of the residual stream into one half of the [K*T, 2C]
  * DPT input slot + fp32 camera-token copy (omnivggt_aggregator.py:273-303,:248-251; camera_head.py:96-99). */
@@ -247,6 +256,32 @@ long long ovg_camera_workspace_bytes(const ovg_camera* h, int K);
 /* cam_tokens fp32 [B*S, D]; out fp32 [iters, B*S, 9]: the activated pose encoding after each iteration. */
 int ovg_camera_forward(ovg_camera* h, const float* cam_tokens, int B, int S, int iters, float* out, void* workspace,
                        long long workspace_bytes, void* stream);
+
+/* Cross-GPU barrier on peer-mapped flags (no NCCL, no host): the rank bumps its private device counter `epoch_counter`,
+ * writes the new value into slot `rank` of every peer's flag array (int[world], peer-mapped, zero-initialised) and waits until
+ * all slots of its own array have reached it.  Orders the peer stores of the kernels launched before it on this stream against
+ * the peers' reads launched after their barrier.  All ranks must execute the same sequence of barriers. */
+int ovg_peer_barrier(int* const* flag_peers, int* epoch_counter, int rank, int world, void* stream);
+
+/* Context-parallel aggregator: ONE scene whose views are sharded over `world` GPUs of a node.
+ * Every rank runs the per-token work (LayerNorm, QKV / proj / MLP GEMMs, frame attention) on its own S views; in the global
+ * blocks (models/aggregator.py:312-341: one SDPA over all views) the QKV epilogue stores the K / V rows of the rank's tokens
+ * straight into every rank's full-length K / V buffer over NVLink (ovg_gemm_args.k_peers), a flag barrier follows, and the
+ * rank's own queries attend to all keys (ovg_attention_kv).  No collective library call on the data path; K / V buffers are
+ * double buffered so that one barrier per global block suffices. */
+typedef struct ovg_context_parallel {
+  int rank; int world;
+  int views_total;                    /* views of the whole scene; this rank holds views [rank*S, rank*S + S), S = views_total / world */
+  void* k_peers[2][8];                /* [buffer][rank]: bf16 [heads, views_total*T, 64] in rank's memory, peer mapped */
+  void* v_peers[2][8];
+  int* flag_peers[8];                 /* [rank]: int[world], peer mapped, zero-initialised once */
+  int* epoch_counter;                 /* private device int, zero-initialised once */
+} ovg_context_parallel;
+/* Same arguments as ovg_aggregator_forward with B = 1 and S = the LOCAL view count; depth_idx are local view indices. */
+int ovg_aggregator_forward_cp(ovg_aggregator* h, const ovg_context_parallel* cp, const float* patch_tokens, const float* inj,
+                              const float* depth, const float* mask, const int* depth_idx, int n_depth, const float* rope_cos,
+                              const float* rope_sin, int maxpos, int S, int H, int W, void* workspace, long long workspace_bytes,
+                              void* const* slots, float* cam_out, void* stream);
 
 /* Timing hook for bench.py: when enabled, every global-attention launch of ovg_aggregator_forward is bracketed by CUDA events
  * on its stream; after a synchronize, ovg_runtime_attention_times() returns the elapsed ms of the launches since the enable. */

@@ -37,6 +37,7 @@ class GemmArgs(C.Structure):
         ("rope_cos", _vp), ("rope_sin", _vp), ("qscale", _f),
         ("w2", _vp), ("b2", _vp), ("outc", _i), ("head_act", _i), ("preds", _vp), ("conf", _vp),
         ("block_n", _i), ("qk_norm", _i), ("rope", _i),
+        ("k_peers", _vp * 8), ("v_peers", _vp * 8), ("n_peers", _i), ("peer_ntok", _i), ("peer_tok_off", _ll),
     ]
 
 
@@ -82,6 +83,12 @@ class CameraDesc(C.Structure):
                 ("fc2_w", _vp), ("fc2_b", _vp)]
 
 
+class ContextParallelDesc(C.Structure):
+    """Mirror of ``ovg_context_parallel``."""
+    _fields_ = [("rank", _i), ("world", _i), ("views_total", _i), ("k_peers", (_vp * 8) * 2), ("v_peers", (_vp * 8) * 2),
+                ("flag_peers", _vp * 8), ("epoch_counter", _vp)]
+
+
 _pp = C.POINTER(_vp)
 EXPORTS = {
     "ovg_version": (C.c_int, []),
@@ -90,9 +97,13 @@ EXPORTS = {
     "ovg_launch_count": (C.c_longlong, []),
     "ovg_gemm": (C.c_int, [C.POINTER(GemmArgs), _vp]),
     "ovg_attention": (C.c_int, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "ovg_attention_kv": (C.c_int, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "ovg_peer_barrier": (C.c_int, [C.POINTER(_vp), _vp, _i, _i, _vp]),
+    "ovg_aggregator_forward_cp": (C.c_int, [_vp, C.POINTER(ContextParallelDesc), _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i,
+                                            _i, _vp, _ll, _pp, _vp, _vp]),
     "ovg_layernorm": (C.c_int, [_vp, _i, _ll, _vp, _i, _ll, _i, _i, _vp, _vp, _f, _i, _i, _i, _vp]),
     "ovg_image_im2col": (C.c_int, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
-    "ovg_assemble_tokens": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "ovg_assemble_tokens": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "ovg_inject_snapshot": (C.c_int, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "ovg_depth_im2col": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "ovg_im2col3x3s2": (C.c_int, [_vp, _vp, _i, _i, _i, _i, _vp]),

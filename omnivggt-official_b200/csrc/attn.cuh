@@ -14,7 +14,8 @@
 namespace ovg {
 
 struct AttnParams {
-  int n;        // sequence length (keys == queries)
+  int n;        // number of query rows per (batch, head)
+  int nkv;      // number of keys / values per (batch, head); == n for self-attention over one buffer
   int heads;
   int C;        // heads * 64 (row stride of `out`)
   __nv_bfloat16* out;  // [batch, n, C]
@@ -108,7 +109,7 @@ attn1_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
   const int q0 = blockIdx.x * 128;
   const int head = blockIdx.y;
   const int bh = blockIdx.z * p.heads + head;
-  const int nkv = (p.n + 127) / 128;
+  const int nkv = (p.nkv + 127) / 128;
 
   if (warp == 0 && lane == 0) {
     if (smem_u32(smem) & 1023u) {
@@ -225,7 +226,7 @@ attn1_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
     float m_used = -INFINITY;
     float l = 0.f;
     for (int j = 0; j < nkv; ++j) {
-      const int kv_valid = min(128, p.n - j * 128);
+      const int kv_valid = min(128, p.nkv - j * 128);
       mbar_wait_quiet(s_full, j & 1);
       tc_fence_after();
       uint32_t raw[128];

@@ -137,12 +137,13 @@ struct AssembleParams {
   const float* placeholder;  // [C]
   const int* has_depth;      // [K]
   int K, S, T, R, C;
+  int view_base;             // scene-local index of frame 0 (non-zero only when a scene's views are sharded over ranks)
 };
 
 __global__ void assemble_tokens_kernel(const AssembleParams p) {
   const int row = blockIdx.x;
   const int k = row / p.T, t = row % p.T;
-  const int slot = (k % p.S) == 0 ? 0 : 1;
+  const int slot = ((k % p.S) + p.view_base) == 0 ? 0 : 1;
   const int P = p.T - p.R - 1;
   for (int c = threadIdx.x * 4; c < p.C; c += blockDim.x * 4) {
     float4 o;
@@ -282,7 +283,10 @@ __global__ void __launch_bounds__(256) depth_scale_kernel(const DepthParams p) {
 
 // Stage 3: one block per (scene, selected view, patch row): the 14 image rows are read as coalesced float2 runs, every pair
 // lands in one patch (the patch size is even) and is stored as one bf16x2.
-__global__ void __launch_bounds__(256) depth_im2col_kernel(const DepthParams p) {
+template <int PATCH>      // compile-time patch size (0: runtime p.patch): the index arithmetic is half of this kernel's instructions
+__global__ void __launch_bounds__(256) depth_im2col_kernel(const DepthParams pin) {
+  DepthParams p = pin;
+  if (PATCH > 0) p.patch = PATCH;
   const int hp = p.H / p.patch, wp = p.W / p.patch;
   const int py = blockIdx.x % hp, j = (blockIdx.x / hp) % p.Sd, b = blockIdx.x / (hp * p.Sd);
   const float scale = reinterpret_cast<const float*>(p.partial + static_cast<long long>(p.B) * DEPTH_NCHUNK * 2)[b];
@@ -312,7 +316,10 @@ struct ImageColParams {
   float mean[3], istd[3];
 };
 
-__global__ void __launch_bounds__(256) image_im2col_kernel(const ImageColParams p) {
+template <int PATCH>
+__global__ void __launch_bounds__(256) image_im2col_kernel(const ImageColParams pin) {
+  ImageColParams p = pin;
+  if (PATCH > 0) p.patch = PATCH;
   const int hp = p.H / p.patch, wp = p.W / p.patch;
   const int py = blockIdx.x % hp, k = blockIdx.x / hp;
   const int w2 = p.W / 2, pp = p.patch * p.patch;
@@ -482,6 +489,38 @@ __global__ void __launch_bounds__(256) upsample_rows_kernel(const UpsampleParams
       out.w = pack_bf16(r[6], r[7]);
     }
     *reinterpret_cast<uint4*>(drow + static_cast<size_t>(X) * p.C + v * 8) = out;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Cross-GPU barrier on peer-mapped flags (context-parallel global attention): the K / V rows a rank stored into its peers'
+// buffers (QKV epilogue of the kernels before this one on the stream) become visible before any peer's attention reads them.
+struct PeerBarrierParams {
+  int* flags[8];     // flags[r]: int[world] in rank r's memory (peer mapped)
+  int* epoch;        // this rank's private barrier counter (device memory): every barrier uses the next value, so a captured
+                     // CUDA graph can be replayed (no epoch baked into the launch)
+  int rank, world;
+};
+__global__ void peer_barrier_kernel(const PeerBarrierParams p) {
+  const int t = threadIdx.x;
+  __shared__ int s_epoch;
+  if (t == 0) {
+    s_epoch = *p.epoch + 1;
+    *p.epoch = s_epoch;
+  }
+  __syncthreads();
+  const int epoch = s_epoch;
+  if (t < p.world) {
+    __threadfence_system();                                   // peer stores of earlier kernels are complete at kernel end; order the flag after them
+    volatile int* remote = p.flags[t] + p.rank;
+    *remote = epoch;
+    __threadfence_system();
+    volatile int* mine = p.flags[p.rank] + t;
+    long long spins = 0;
+    while (*mine < epoch) {
+      if (++spins > 2000000000LL) __trap();                   // a rank that never arrives must not hang the box silently
+    }
+    __threadfence_system();
   }
 }
 

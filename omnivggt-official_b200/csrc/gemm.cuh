@@ -54,6 +54,13 @@ struct GemmParams {
   float qscale;  // softmax scale * log2(e), folded into q
   int qk_norm;   // 1: LayerNorm(64) on q,k (aggregator blocks); 0: plain (DINOv2 blocks)
   int rope;      // 1: 2-D RoPE on q,k
+  // context parallelism: K and V rows of this rank's tokens are stored into every rank's full-length K / V buffer
+  // ([batch*heads, peer_ntok, 64], this rank's tokens starting at row peer_tok_off) instead of k_out / v_out
+  __nv_bfloat16* k_peer[8];
+  __nv_bfloat16* v_peer[8];
+  int n_peers;
+  int peer_ntok;
+  long long peer_tok_off;
   // ---- EPI_HEADTAIL (heads/dpt_head.py:121-126 + heads/head_act.py:61-112): relu, 1x1 32->outc, activation
   const float* w2;  // [outc][32]
   const float* b2;  // [outc]
@@ -230,22 +237,28 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const uint32_
           continue;
         }
         if (m >= p.M) continue;
-        __nv_bfloat16* dst = (which == 0 ? p.q_out : (which == 1 ? p.k_out : p.v_out)) +
-                             ((seq * heads + h) * p.ntok + tok) * 64;
-        uint4* d4 = reinterpret_cast<uint4*>(dst);
+        uint4 o8[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          uint4 o;
-          o.x = pack_bf16(v2[4 * i + 0].x, v2[4 * i + 0].y);
-          o.y = pack_bf16(v2[4 * i + 1].x, v2[4 * i + 1].y);
-          o.z = pack_bf16(v2[4 * i + 2].x, v2[4 * i + 2].y);
-          o.w = pack_bf16(v2[4 * i + 3].x, v2[4 * i + 3].y);
-#ifdef OVG_QKV_NOSTORE
-          if (o.x == 0x12345678u) d4[i] = o;
-#else
-          d4[i] = o;
-#endif
+          o8[i].x = pack_bf16(v2[4 * i + 0].x, v2[4 * i + 0].y);
+          o8[i].y = pack_bf16(v2[4 * i + 1].x, v2[4 * i + 1].y);
+          o8[i].z = pack_bf16(v2[4 * i + 2].x, v2[4 * i + 2].y);
+          o8[i].w = pack_bf16(v2[4 * i + 3].x, v2[4 * i + 3].y);
         }
+        if (which > 0 && p.n_peers > 0) {
+          // one 128-byte row per lane into every rank's buffer: plain stores over NVLink (peer-mapped memory)
+          const long long roff = ((seq * heads + h) * p.peer_ntok + p.peer_tok_off + tok) * 64;
+          for (int pr = 0; pr < p.n_peers; ++pr) {
+            uint4* d4 = reinterpret_cast<uint4*>((which == 1 ? p.k_peer[pr] : p.v_peer[pr]) + roff);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) d4[i] = o8[i];
+          }
+          continue;
+        }
+        uint4* d4 = reinterpret_cast<uint4*>((which == 0 ? p.q_out : (which == 1 ? p.k_out : p.v_out)) +
+                                             ((seq * heads + h) * p.ntok + tok) * 64);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) d4[i] = o8[i];
       }
     }
   } else {

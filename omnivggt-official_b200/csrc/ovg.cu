@@ -223,7 +223,7 @@ extern "C" {
 
 void ovg_debug_set_attn_profile(long long* buf) { g_attn_prof = buf; }
 
-int ovg_version(void) { return 1; }
+int ovg_version(void) { return 2; }
 const char* ovg_last_error(void) { return g_err.c_str(); }
 long long ovg_launch_count(void) { return g_launches.load(); }
 
@@ -292,6 +292,17 @@ int ovg_gemm(const ovg_gemm_args* a, void* stream) {
   p.head_act = a->head_act;
   p.preds = a->preds;
   p.conf = a->conf;
+  p.n_peers = a->epi == OVG_EPI_QKV ? a->n_peers : 0;
+  p.peer_ntok = a->peer_ntok;
+  p.peer_tok_off = a->peer_tok_off;
+  OVG_REQUIRE(p.n_peers >= 0 && p.n_peers <= 8, "at most 8 peers");
+  for (int i = 0; i < p.n_peers; ++i) {
+    OVG_REQUIRE(a->k_peers[i] && a->v_peers[i], "null peer buffer");
+    p.k_peer[i] = reinterpret_cast<__nv_bfloat16*>(a->k_peers[i]);
+    p.v_peer[i] = reinterpret_cast<__nv_bfloat16*>(a->v_peers[i]);
+  }
+  if (p.n_peers > 0) OVG_REQUIRE(a->peer_ntok >= a->ntok && a->peer_tok_off >= 0 && a->peer_tok_off + a->ntok <= a->peer_ntok,
+                                 "peer token window");
 
   int bn = a->block_n;
   if (a->epi == OVG_EPI_HEADTAIL) {
@@ -312,7 +323,7 @@ int ovg_gemm(const ovg_gemm_args* a, void* stream) {
     }
   }
   if (a->epi == OVG_EPI_QKV) {
-    OVG_REQUIRE(a->q_out && a->k_out && a->v_out && a->bias, "QKV args");
+    OVG_REQUIRE(a->q_out && a->bias && ((a->k_out && a->v_out) || a->n_peers > 0), "QKV args");
     if (a->qk_norm) OVG_REQUIRE(a->qn_w && a->qn_b && a->kn_w && a->kn_b, "QKV q/k norm weights");
     if (a->rope) OVG_REQUIRE(a->rope_cos && a->rope_sin && a->maxpos > 0 && a->maxpos <= 64 && a->wp > 0,
                              "QKV rope table (maxpos <= 64)");
@@ -358,7 +369,7 @@ int ovg_gemm(const ovg_gemm_args* a, void* stream) {
       rc = get_out_map(a->out, a->epi == OVG_EPI_RESID, a->n, a->m, a->ldo, &to[0]);
       if (rc) return rc;
       p.staged = 1;
-    } else if (g_stage_default && a->epi == OVG_EPI_QKV) {
+    } else if (g_stage_default && a->epi == OVG_EPI_QKV && a->n_peers == 0) {
       // head-major q / k / v [batch * heads, ntok, 64]: one 32-token x 64 box per bulk store
       const unsigned long long bh = static_cast<unsigned long long>(a->m / a->ntok) * (a->C / 64);
       const void* outs[3] = {a->q_out, a->k_out, a->v_out};
@@ -416,17 +427,18 @@ int ovg_gemm(const ovg_gemm_args* a, void* stream) {
   }
 }
 
-int ovg_attention(const void* q, const void* k, const void* v, void* out, int batch, int heads, int n, void* stream) {
+int ovg_attention_kv(const void* q, const void* k, const void* v, void* out, int batch, int heads, int nq, int nkv,
+                     void* stream) {
   OVG_REQUIRE(q && k && v && out, "null operand");
-  OVG_REQUIRE(batch > 0 && heads > 0 && n > 0, "empty problem");
+  OVG_REQUIRE(batch > 0 && heads > 0 && nq > 0 && nkv > 0, "empty problem");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   CUtensorMap tq, tk, tv;
   const unsigned long long bh = static_cast<unsigned long long>(batch) * heads;
-  int rc = get_map(q, 64, n, bh, 64, 128, &tq);
+  int rc = get_map(q, 64, nq, bh, 64, 128, &tq);
   if (rc) return rc;
-  rc = get_map(k, 64, n, bh, 64, 128, &tk);
+  rc = get_map(k, 64, nkv, bh, 64, 128, &tk);
   if (rc) return rc;
-  rc = get_map(v, 64, n, bh, 64, 128, &tv);
+  rc = get_map(v, 64, nkv, bh, 64, 128, &tv);
   if (rc) return rc;
   static PerDeviceOnce once;
   if (once.needed()) {
@@ -434,10 +446,14 @@ int ovg_attention(const void* q, const void* k, const void* v, void* out, int ba
     OVG_CUDA(cudaFuncSetAttribute(ovg::attn1_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     once.mark_done();
   }
-  ovg::AttnParams p{n, heads, heads * 64, reinterpret_cast<__nv_bfloat16*>(out), g_attn_prof};
-  dim3 grid1((n + 127) / 128, heads, batch);
+  ovg::AttnParams p{nq, nkv, heads, heads * 64, reinterpret_cast<__nv_bfloat16*>(out), g_attn_prof};
+  dim3 grid1((nq + 127) / 128, heads, batch);
   ovg::attn1_kernel<<<grid1, ovg::ATT1_THREADS, ovg::ATT1_SMEM_BYTES, st>>>(tq, tk, tv, p);
   return post_launch("ovg_attention");
+}
+
+int ovg_attention(const void* q, const void* k, const void* v, void* out, int batch, int heads, int n, void* stream) {
+  return ovg_attention_kv(q, k, v, out, batch, heads, n, n, stream);
 }
 
 int ovg_layernorm(const void* in, int in_is_bf16, long long ld_in, void* out, int out_is_f32, long long ld_out, int rows,
@@ -467,14 +483,26 @@ int ovg_layernorm(const void* in, int in_is_bf16, long long ld_in, void* out, in
 }
 
 int ovg_assemble_tokens(float* x, const float* patch, const float* cam_tok, const float* reg_tok, const float* inj0,
-                        const float* placeholder, const int* has_depth, int K, int S, int T, int R, int C,
+                        const float* placeholder, const int* has_depth, int K, int S, int T, int R, int C, int view_base,
                         void* stream) {
   OVG_REQUIRE(x && patch && cam_tok && reg_tok && inj0 && placeholder && has_depth, "null operand");
   OVG_REQUIRE(K > 0 && S > 0 && K % S == 0 && T > R + 1 && C % 4 == 0, "bad geometry");
-  ovg::AssembleParams p{x, patch, cam_tok, reg_tok, inj0, placeholder, has_depth, K, S, T, R, C};
+  ovg::AssembleParams p{x, patch, cam_tok, reg_tok, inj0, placeholder, has_depth, K, S, T, R, C, view_base};
   const int threads = C / 4 < 256 ? ((C / 4 + 31) / 32) * 32 : 256;
   ovg::assemble_tokens_kernel<<<K * T, threads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
   return post_launch("ovg_assemble_tokens");
+}
+
+int ovg_peer_barrier(int* const* flag_peers, int* epoch_counter, int rank, int world, void* stream) {
+  OVG_REQUIRE(flag_peers && epoch_counter && world >= 1 && world <= 8 && rank >= 0 && rank < world, "bad arguments");
+  ovg::PeerBarrierParams p{};
+  for (int i = 0; i < world; ++i) {
+    OVG_REQUIRE(flag_peers[i], "null flag array");
+    p.flags[i] = flag_peers[i];
+  }
+  p.epoch = epoch_counter; p.rank = rank; p.world = world;
+  ovg::peer_barrier_kernel<<<1, 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  return post_launch("ovg_peer_barrier");
 }
 
 int ovg_inject_snapshot(float* x, const float* inj, void* slot, float* cam_out, int K, int T, int C, int coff,
@@ -502,7 +530,8 @@ int ovg_depth_im2col(const float* depth, const float* mask, const int* idx, doub
   ovg::depth_scale_kernel<<<B, 256, 0, st>>>(p);
   rc = post_launch("ovg_depth_im2col(scale)");
   if (rc) return rc;
-  ovg::depth_im2col_kernel<<<B * Sd * (H / patch), 256, 0, st>>>(p);
+  if (patch == 14) ovg::depth_im2col_kernel<14><<<B * Sd * (H / patch), 256, 0, st>>>(p);
+  else ovg::depth_im2col_kernel<0><<<B * Sd * (H / patch), 256, 0, st>>>(p);
   return post_launch("ovg_depth_im2col");
 }
 
@@ -517,7 +546,8 @@ int ovg_image_im2col(const float* images, const float* mean3, const float* std3,
     p.mean[c] = mean3[c];
     p.istd[c] = 1.0f / std3[c];
   }
-  ovg::image_im2col_kernel<<<K * (H / patch), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  if (patch == 14) ovg::image_im2col_kernel<14><<<K * (H / patch), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  else ovg::image_im2col_kernel<0><<<K * (H / patch), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
   return post_launch("ovg_image_im2col");
 }
 

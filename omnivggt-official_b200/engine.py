@@ -311,8 +311,9 @@ class Engine:
     # ------------------------------------------------------------------------------------------ aggregator
     def aggregate(self, patch_tokens: torch.Tensor, inj: torch.Tensor, depth: Optional[torch.Tensor],
                   mask: Optional[torch.Tensor], depth_idx: List[int], B: int, S: int, H: int, W: int,
-                  keep: Sequence[int]):
-        """patch_tokens fp32 [K,P,C]; inj fp32 [depth+1,K,C].  Returns ({layer: bf16 slot [K,T,2C]}, cam fp32 [K,2C])."""
+                  keep: Sequence[int], cp=None, views_total: int = 0):
+        """patch_tokens fp32 [K,P,C]; inj fp32 [depth+1,K,C].  Returns ({layer: bf16 slot [K,T,2C]}, cam fp32 [K,2C]).
+        ``cp`` (a ContextParallel): B = 1, S = this rank's views of a scene with ``views_total`` views."""
         lib = L.lib()
         Cc, R = self.C, self.R
         K = B * S
@@ -333,9 +334,16 @@ class Engine:
         slot_p = (C.c_void_p * 4)(*[t.data_ptr() for t in slot_t])
         cam_out = self.ws.get("cam_out", (K, 2 * Cc), F32)
         pt, ij = patch_tokens.contiguous(), inj.contiguous()
-        L.check(lib.ovg_aggregator_forward(self.h_agg, pt.data_ptr(), ij.data_ptr(), L.ptr(d32), L.ptr(m32), L.ptr(idx), Sd,
-                                           cos.data_ptr(), sin.data_ptr(), cos.shape[0], B, S, H, W, wsb.data_ptr(), wsb.numel(),
-                                           slot_p, cam_out.data_ptr(), L.stream()))
+        if cp is not None:
+            assert B == 1, "context parallelism shards the views of one scene"
+            cd = cp.desc(self.heads, views_total * T, views_total)
+            L.check(lib.ovg_aggregator_forward_cp(self.h_agg, C.byref(cd), pt.data_ptr(), ij.data_ptr(), L.ptr(d32), L.ptr(m32),
+                                                  L.ptr(idx), Sd, cos.data_ptr(), sin.data_ptr(), cos.shape[0], S, H, W,
+                                                  wsb.data_ptr(), wsb.numel(), slot_p, cam_out.data_ptr(), L.stream()))
+        else:
+            L.check(lib.ovg_aggregator_forward(self.h_agg, pt.data_ptr(), ij.data_ptr(), L.ptr(d32), L.ptr(m32), L.ptr(idx), Sd,
+                                               cos.data_ptr(), sin.data_ptr(), cos.shape[0], B, S, H, W, wsb.data_ptr(),
+                                               wsb.numel(), slot_p, cam_out.data_ptr(), L.stream()))
         return dict(zip(self.keep, slot_t)), cam_out
 
     # ------------------------------------------------------------------------------------------ camera head

@@ -64,6 +64,7 @@ class OmniVGGT(nn.Module, PyTorchModelHubMixin):
         if init_seed is not None:
             init_parameters(self, init_seed, dezero=False)
         self._engine = None
+        self._cp = None                     # ContextParallel state (enable_context_parallel)
         object.__setattr__(self, "_dino_lp", None)   # low-precision replica of the frozen patchifier (lazy, not in state_dict)
 
     # ---------------------------------------------------------------------------------------------- packing
@@ -132,9 +133,54 @@ class OmniVGGT(nn.Module, PyTorchModelHubMixin):
             assert extrinsics is not None and intrinsics is not None, "camera_gt_index given without cameras"
         eng = self.engine()
         args = (images, extrinsics, intrinsics, depth, mask, depth_idx, cam_idx)
+        if self._cp is not None:
+            return self._forward_cp(eng, *args)
         if self.use_cuda_graph and images.is_cuda and not torch.cuda.is_current_stream_capturing():
             return self._forward_graphed(eng, *args)
         return self._forward_impl(eng, *args)
+
+    # ---------------------------------------------------------------------------------------------- context parallelism
+    def enable_context_parallel(self, group=None) -> "OmniVGGT":
+        """Shard the VIEWS of one scene over the ranks of a torch.distributed group on one node.
+        Every rank then calls forward() with the SAME full inputs (B = 1, S divisible by the world size) and gets the dense
+        predictions of ITS views (``view_range``) plus the pose encodings of all views.  See context_parallel.py."""
+        from .context_parallel import ContextParallel
+        self._cp = ContextParallel(next(self.parameters()).device, group)
+        return self
+
+    def _forward_cp(self, eng, images, extrinsics, intrinsics, depth, mask, depth_idx, cam_idx):
+        cp = self._cp
+        B, S, Cin, H, W = images.shape
+        if B != 1:
+            raise ValueError("context parallelism shards the views of ONE scene (B = 1); use scene-level data parallelism for batches")
+        v0, n = cp.local_views(S)
+        sl = slice(v0, v0 + n)
+        ag = self.aggregator
+        if eng.dino is None:
+            raise RuntimeError("context parallelism runs the DINOv2 patchifier on the libovg runtime (dino_backend='ovg')")
+        P = (H // self.patch_size) * (W // self.patch_size)
+        pos = TP.dino_pos_embed(ag.patch_embed, P, H, W, self.patch_size).float()
+        patch = eng.dino_patchify(images[0, sl].float().contiguous(), pos, _RESNET_MEAN, _RESNET_STD)
+        # camera aux: pose normalisation is global over the selected views (omnivggt_aggregator.py:85-105), the inputs are a
+        # few hundred bytes per view and replicated, so every rank computes all injection vectors and keeps its columns
+        pose = rows = None
+        if len(cam_idx):
+            ci = eng.cached(("cam_idx", tuple(cam_idx)), lambda: torch.tensor(cam_idx))
+            rows = eng.cached(("cam_rows", 1, S, tuple(cam_idx)), lambda: torch.tensor(cam_idx))
+            pose = TP.aux_pose_encoding(extrinsics.index_select(1, ci), intrinsics.index_select(1, ci), H, W)
+        inj = TP.injection_vectors(eng.inj_pack, pose, cam_idx, 1, S, rows)[:, sl].contiguous()
+        didx = cp.local_indices(depth_idx, S)
+        d_loc = depth[:, sl] if len(didx) else None
+        m_loc = mask[:, sl] if len(didx) else None
+        slots, cam_loc = eng.aggregate(patch, inj, d_loc, m_loc, didx, 1, n, H, W, set(self.dpt_layers), cp=cp, views_total=S)
+        cam_all = cp.all_gather_rows(cam_loc)                       # [S, 2C]: the camera head attends across all views
+        pose_list = self._camera(eng, cam_all, 1, S)
+        eng.warm_tables(H, W)
+        d_out = eng.dpt("depth_head", slots, self.dpt_layers, n, H, W, head_act=0)
+        p_out = eng.dpt("point_head", slots, self.dpt_layers, n, H, W, head_act=1)
+        return {"pose_enc": pose_list[-1], "pose_enc_list": pose_list, "depth": d_out[0].view(1, n, H, W, 1),
+                "depth_conf": d_out[1].view(1, n, H, W), "world_points": p_out[0].view(1, n, H, W, 3),
+                "world_points_conf": p_out[1].view(1, n, H, W), "images": images[:, sl], "view_range": (v0, v0 + n)}
 
     # ---------------------------------------------------------------------------------------------- post-processing
     @torch.no_grad()

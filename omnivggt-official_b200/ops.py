@@ -89,6 +89,15 @@ def attention(q, k, v, out, batch: int, heads: int, n: int):
     return out
 
 
+def attention_kv(q, k, v, out, batch: int, heads: int, nq: int, nkv: int):
+    """q [batch, heads, nq, 64] against k, v [batch, heads, nkv, 64] -> out [batch, nq, heads*64]."""
+    for t, nm in ((q, "q"), (k, "k"), (v, "v"), (out, "out")):
+        _chk(t, BF16, nm)
+        assert t.is_contiguous()
+    L.check(L.lib().ovg_attention_kv(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), batch, heads, nq, nkv, L.stream()))
+    return out
+
+
 def layernorm(x, out, w=None, b=None, eps=1e-5, rows=None, grp_out=0, grp_in=0, grp_off=0):
     assert x.dtype in (F32, BF16) and out.dtype in (F32, BF16) and x.stride(-1) == 1 and out.stride(-1) == 1
     x2 = x if x.dim() == 2 else x.reshape(-1, x.shape[-1])
@@ -100,10 +109,10 @@ def layernorm(x, out, w=None, b=None, eps=1e-5, rows=None, grp_out=0, grp_in=0, 
     return out
 
 
-def assemble_tokens(x, patch, cam_tok, reg_tok, inj0, placeholder, has_depth, K, S, T, R, C):
+def assemble_tokens(x, patch, cam_tok, reg_tok, inj0, placeholder, has_depth, K, S, T, R, C, view_base: int = 0):
     L.check(L.lib().ovg_assemble_tokens(x.data_ptr(), patch.data_ptr(), cam_tok.data_ptr(), reg_tok.data_ptr(),
                                         inj0.data_ptr(), placeholder.data_ptr(), has_depth.data_ptr(), K, S, T, R, C,
-                                        L.stream()))
+                                        view_base, L.stream()))
 
 
 def inject_snapshot(x, inj, slot, cam_out, K, T, C, coff):

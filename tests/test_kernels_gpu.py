@@ -418,3 +418,23 @@ def test_head_tail(outc, act):
     pr = torch.exp(y[..., :-1]) if act == 0 else torch.sign(y[..., :-1]) * torch.expm1(y[..., :-1].abs())
     torch.cuda.synchronize()
     assert rel(preds, pr) < 1e-2 and rel(conf, 1 + y[..., -1].exp()) < 1e-2
+
+
+# ----------------------------------------------------------------------------------------------- C host
+def test_c_host_drives_the_runtime(tmp_path):
+    """A plain C program (tests/c/runtime_identity.c: gcc, libovg + libcudart, no Python / torch in the process) runs the
+    aggregator through the handle-level C ABI with raw device pointers; with zero block weights the kept intermediates must
+    equal the assembled tokens bit for bit."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, "omnivggt-official_b200")
+    exe = str(tmp_path / "runtime_identity")
+    cuda_lib = "/usr/local/cuda/lib64"
+    subprocess.check_call(["gcc", os.path.join(root, "tests", "c", "runtime_identity.c"), "-I", os.path.join(root, "include"),
+                           "-L", pkg, "-lovg", "-L", cuda_lib, "-lcudart", "-lm", f"-Wl,-rpath,{pkg}", f"-Wl,-rpath,{cuda_lib}",
+                           "-o", exe])
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    print(r.stdout, r.stderr)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "0 mismatches" in r.stdout
