@@ -4,10 +4,10 @@
 //
 // q is pre-scaled by (1/sqrt(64))*log2(e) in the QKV GEMM epilogue, so probabilities are exp2(s - m).
 //
-// Online softmax with a stale reference and lazy rescaling: P(j) = exp2(S - m_ref) is computed against
-// the reference left by earlier steps while this step's row maximum is gathered in the same pass; O / l are rescaled
-// (and the chunk redone from the S values still in registers) only when the maximum exceeds the reference by > 8 (log2
-// units) -- exact, the reference cancels in O / l, and P stays <= 256.
+// Online softmax with a stale reference and lazy rescaling: P(j) = exp2(S - m_ref) is computed against the reference left
+// by earlier steps; no running maximum is tracked.  bf16 P and the fp32 O / l accumulators carry the full fp32 exponent
+// range, so a stale reference costs no precision (it cancels in O / l) until exp2 comes near overflow: only then -- detected
+// on the row sum -- O / l are rescaled and the step is redone exactly from the S row still held in registers.
 #pragma once
 #include "ptx.cuh"
 
@@ -54,17 +54,11 @@ __device__ __forceinline__ float2 exp2_poly2(float2 x) {
   o.y = __int_as_float(__float_as_int(t.y) * 8388608 + __float_as_int(p.y));
   return o;
 }
-#ifndef OVG_ATT_NOMAX
-#define OVG_ATT_NOMAX 0        // 1: no running row maximum in the fast pass (overflow is detected on the row sum)
-#endif
-#ifndef OVG_ATT_POLY_INTERLEAVE
-#define OVG_ATT_POLY_INTERLEAVE 0   // 1: the polynomial pairs are every 4th pair instead of the last ones of a chunk
-#endif
 #ifndef OVG_ATT_LATE_WAIT
 #define OVG_ATT_LATE_WAIT 1   // P chunks computed before the wait for PV(j-1) (0: wait before the first store, as in round 1)
 #endif
 #ifndef OVG_ATT_EMU_PAIRS
-#define OVG_ATT_EMU_PAIRS 4   // of every 16 element pairs, how many take the polynomial path (0 = all MUFU); 4 measured best
+#define OVG_ATT_EMU_PAIRS 4   // of every 16 element pairs, how many take the polynomial path (0..4; 4 measured best)
 #endif
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
@@ -261,12 +255,9 @@ attn1_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const float r0 = __uint_as_float(raw[c * 32 + 2 * i]), r1 = __uint_as_float(raw[c * 32 + 2 * i + 1]);
-            const bool poly = OVG_ATT_POLY_INTERLEAVE ? ((i & 3) == 3 && (i >> 2) < OVG_ATT_EMU_PAIRS) : (i >= 16 - OVG_ATT_EMU_PAIRS);
-#if OVG_ATT_NOMAX
+            // every 4th pair goes through the FMA-pipe polynomial (interleaved with the MUFU pairs: 607 vs 624 us clustered)
+            const bool poly = (i & 3) == 3 && (i >> 2) < OVG_ATT_EMU_PAIRS;
             if (poly) mx0 = fmaxf(fmaxf(mx0, r0), r1);     // the polynomial's exponent insertion wraps above 2^127: watch its inputs
-#else
-            if (i & 1) mx1 = fmaxf(fmaxf(mx1, r0), r1); else mx0 = fmaxf(fmaxf(mx0, r0), r1);
-#endif
             float2 x = fadd2(make_float2(r0, r1), negm);
             if (poly) {
               x = exp2_poly2(x);
@@ -290,8 +281,7 @@ attn1_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
           }
           tmem_st16(tP + c * 16, pk);
         }
-#if OVG_ATT_NOMAX
-        // No running maximum: bf16 P and the fp32 O / l accumulators carry the full fp32 exponent range, so a stale reference
+        // No running maximum (612 vs 624 us): bf16 P and the fp32 O / l accumulators carry the full fp32 exponent range, so a stale reference
         // costs no precision until exp2 overflows.  The step is redone (exactly, from the S row in registers) only if the row
         // sum says a probability came near the top of that range, or a polynomial lane saw an input it cannot represent.
         slow = __any_sync(0xffffffffu, !(acc.x + acc.y < 1e30f) || (mx0 - m_used) > 100.0f);
@@ -303,10 +293,6 @@ attn1_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
           }
           m_new = fmaxf(m_used, fmaxf(mx0, mx1));
         }
-#else
-        m_new = fmaxf(m_used, fmaxf(mx0, mx1));
-        slow = __any_sync(0xffffffffu, (m_new - m_used) > 8.0f);
-#endif
       }
       if (slow) {
         if (j == 0) {
