@@ -238,6 +238,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS))
     ap.add_argument("--scene-batch", type=int, default=4, help="cfg4: scenes per forward call")
+    ap.add_argument("--cp", action="store_true", help="context parallelism: ONE scene per step, its views sharded over the ranks")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-torch-baseline", action="store_true")
     args = ap.parse_args()
@@ -271,7 +272,12 @@ def main():
     lib = _lib.lib()
 
     # ---- this rank's share of the workload: `calls` forward calls of `Bm` scenes each per step
-    if cfg["scaling"] == "strong":
+    if args.cp:
+        # one scene per step for the whole job: every rank gets the full (replicated) inputs and computes its views
+        assert cfg["scenes"] == 1 and S % world == 0, "--cp shards the views of a single-scene config over the ranks"
+        model.enable_context_parallel()
+        Bm, calls, total_scenes = 1, 1, 1
+    elif cfg["scaling"] == "strong":
         mine = shard_scenes(cfg["scenes"], rank, world)
         Bm = max(1, min(args.scene_batch, len(mine)))
         while len(mine) % Bm:
@@ -283,7 +289,7 @@ def main():
         total_scenes = world
     need_d, need_c = len(cfg["depth_idx"]) > 0, len(cfg["cam_idx"]) > 0
     in_keys = ["images"] + (["depth", "mask"] if need_d else []) + (["extrinsics", "intrinsics"] if need_c else [])
-    host_in = [{k: v.pin_memory() for k, v in synth_inputs(Bm, S, seed=1 + rank * 64 + c).items() if k in in_keys}
+    host_in = [{k: v.pin_memory() for k, v in synth_inputs(Bm, S, seed=1 + (0 if args.cp else rank * 64) + c).items() if k in in_keys}
                for c in range(calls)]
     dev_in = [{k: v.to(dev) for k, v in h.items()} for h in host_in]
     idx_kw = dict(depth_gt_index=list(cfg["depth_idx"]), camera_gt_index=list(cfg["cam_idx"]))
@@ -358,6 +364,8 @@ def main():
     peak_tf, peak_hbm, peak_src = measured_peaks()
     L = S * T_TOK
     att_flops = 4.0 * Bm * L * L * 1024               # 4 L^2 C per scene and launch (QK^T + PV, 16 heads x 64)
+    if args.cp:
+        att_flops /= world                            # a rank's own queries (L / world rows) against all L keys
     att_avg = sum(att_ms) / max(len(att_ms), 1)
     achieved = att_flops / (att_avg * 1e-3) / 1e12
     traffic = None
@@ -371,16 +379,18 @@ def main():
                 "timed_in": "separate eager pass of the same K steps (launches inside the replayed CUDA graph cannot be bracketed)"}
 
     line = {"metric": "view_sets_per_sec", "value": value, "unit": "view-sets/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": cfg["scaling"],
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if args.cp else cfg["scaling"],
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": cfg["desc"], "name": args.config, "views": S,
                        "scenes_per_step_all_ranks": total_scenes, "scenes_per_forward_call": Bm, "forward_calls_per_step_per_rank": calls,
                        "depth_gt_index": cfg["depth_idx"], "camera_gt_index": cfg["cam_idx"],
-                       "parallelism": f"dp{world} (scene-sharded, NCCL weight broadcast {bcast_bytes} B at start-up)",
+                       "parallelism": (f"cp{world}: views of one scene sharded over the ranks; K/V rows exchanged by peer stores from the QKV "
+                                       f"epilogue + flag barrier, no collective on the data path" if args.cp else
+                                       f"dp{world} (scene-sharded, NCCL weight broadcast {bcast_bytes} B at start-up)"),
                        "weights": "random-init, full architecture (1217.5 M params)",
                        "l2": "no flush needed: each step streams >2 GB of weights+activations, far beyond the 126 MB L2",
                        "dino": "frozen DINOv2 patchifier on the libovg kernels",
-                       "launch": "CUDA graph replay" if model.use_cuda_graph else "eager"},
+                       "launch": "eager (C++ runtime sequences)" if (args.cp or not model.use_cuda_graph) else "CUDA graph replay"},
             "clocks": clocks,
             "e2e": {"value": total_scenes * 1e3 / e2e_ms, "unit": "view-sets/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms},
@@ -392,7 +402,7 @@ def main():
         est, parts = cb.sample(S)
         line["cpu_baseline"] = {"value": 1.0 / est, "unit": "view-sets/s", "cores": _t.get_num_threads(), "kind": "port",
                                 "sample": cb.SAMPLE_DESC, "seconds_per_view_set": est}
-    if rank == 0 and world == 1 and not args.no_gpu_torch_baseline and Bm == 1:
+    if rank == 0 and world == 1 and not args.no_gpu_torch_baseline and Bm == 1 and not args.cp:
         try:
             ours = model(**dev_in[0], **idx_kw)
             full_in = {k: v.to(dev) for k, v in synth_inputs(1, S, seed=1).items()}

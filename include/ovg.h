@@ -114,6 +114,11 @@ int ovg_inject_snapshot(float* x, const float* inj, void* slot, float* cam_out, 
  * (2*patch*patch wide, row stride ldc) for the patch-embedding GEMM (omnivggt_aggregator.py:107-128,:189-199;
  * layers/patch_embed.py:65-77).  scratch: OVG_DEPTH_SCRATCH_DOUBLES(B) doubles of device memory. */
 #define OVG_DEPTH_SCRATCH_DOUBLES(B) ((B) * (2 * 1024 + 1))
+/* Same with separate view lists: the normalisation mean is taken over the views idx_stats[0..n_stats) (ALL selected views of
+ * the scene, omnivggt_aggregator.py:118-126), rows are produced for the views idx_cols[0..n_cols) only (the views this rank
+ * owns when a scene is sharded over ranks; n_cols may be 0). */
+int ovg_depth_im2col2(const float* depth, const float* mask, const int* idx_stats, int n_stats, const int* idx_cols, int n_cols,
+                      double* scratch, void* cols, int ldc, int B, int S, int H, int W, int patch, void* stream);
 int ovg_depth_im2col(const float* depth, const float* mask, const int* idx, double* scratch, void* cols, int ldc,
                      int B, int S, int Sd, int H, int W, int patch, void* stream);
 
@@ -277,11 +282,14 @@ typedef struct ovg_context_parallel {
   int* flag_peers[8];                 /* [rank]: int[world], peer mapped, zero-initialised once */
   int* epoch_counter;                 /* private device int, zero-initialised once */
 } ovg_context_parallel;
-/* Same arguments as ovg_aggregator_forward with B = 1 and S = the LOCAL view count; depth_idx are local view indices. */
+/* As ovg_aggregator_forward with B = 1 and S = the LOCAL view count, except for the depth modality, whose normalisation is
+ * global over the scene: depth / mask are the FULL tensors [1, views_total, H, W], depth_idx lists ALL selected views (scene
+ * indices, n_depth of them) and depth_idx_local the selected views this rank owns (scene indices, n_depth_local of them). */
 int ovg_aggregator_forward_cp(ovg_aggregator* h, const ovg_context_parallel* cp, const float* patch_tokens, const float* inj,
-                              const float* depth, const float* mask, const int* depth_idx, int n_depth, const float* rope_cos,
-                              const float* rope_sin, int maxpos, int S, int H, int W, void* workspace, long long workspace_bytes,
-                              void* const* slots, float* cam_out, void* stream);
+                              const float* depth, const float* mask, const int* depth_idx, int n_depth,
+                              const int* depth_idx_local, int n_depth_local, const float* rope_cos, const float* rope_sin,
+                              int maxpos, int S, int H, int W, void* workspace, long long workspace_bytes, void* const* slots,
+                              float* cam_out, void* stream);
 
 /* Timing hook for bench.py: when enabled, every global-attention launch of ovg_aggregator_forward is bracketed by CUDA events
  * on its stream; after a synchronize, ovg_runtime_attention_times() returns the elapsed ms of the launches since the enable. */

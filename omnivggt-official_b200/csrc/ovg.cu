@@ -515,24 +515,34 @@ int ovg_inject_snapshot(float* x, const float* inj, void* slot, float* cam_out, 
   return post_launch("ovg_inject_snapshot");
 }
 
-int ovg_depth_im2col(const float* depth, const float* mask, const int* idx, double* scratch, void* cols, int ldc,
-                     int B, int S, int Sd, int H, int W, int patch, void* stream) {
-  OVG_REQUIRE(depth && mask && idx && scratch && cols, "null operand");
-  OVG_REQUIRE(B > 0 && Sd > 0 && Sd <= S && H % patch == 0 && W % patch == 0 && patch % 2 == 0, "bad geometry");
+int ovg_depth_im2col2(const float* depth, const float* mask, const int* idx_stats, int n_stats, const int* idx_cols, int n_cols,
+                      double* scratch, void* cols, int ldc, int B, int S, int H, int W, int patch, void* stream) {
+  OVG_REQUIRE(depth && mask && idx_stats && scratch && (n_cols == 0 || (idx_cols && cols)), "null operand");
+  OVG_REQUIRE(B > 0 && n_stats > 0 && n_stats <= S && n_cols >= 0 && n_cols <= S && H % patch == 0 && W % patch == 0 &&
+                  patch % 2 == 0, "bad geometry");
   OVG_REQUIRE(ldc >= 2 * patch * patch && ldc % 2 == 0, "ldc too small / odd");
   OVG_REQUIRE((reinterpret_cast<uintptr_t>(depth) & 7) == 0 && (reinterpret_cast<uintptr_t>(mask) & 7) == 0 &&
                   (reinterpret_cast<uintptr_t>(cols) & 3) == 0, "depth / mask must be 8-byte aligned");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  ovg::DepthParams p{depth, mask, idx, scratch, reinterpret_cast<__nv_bfloat16*>(cols), ldc, B, S, Sd, H, W, patch};
-  ovg::depth_stats_kernel<<<dim3(ovg::DEPTH_NCHUNK, B), 256, 0, st>>>(p);
+  ovg::DepthParams ps{depth, mask, idx_stats, scratch, reinterpret_cast<__nv_bfloat16*>(cols), ldc, B, S, n_stats, H, W, patch};
+  ovg::depth_stats_kernel<<<dim3(ovg::DEPTH_NCHUNK, B), 256, 0, st>>>(ps);
   int rc = post_launch("ovg_depth_im2col(stats)");
   if (rc) return rc;
-  ovg::depth_scale_kernel<<<B, 256, 0, st>>>(p);
+  ovg::depth_scale_kernel<<<B, 256, 0, st>>>(ps);
   rc = post_launch("ovg_depth_im2col(scale)");
-  if (rc) return rc;
-  if (patch == 14) ovg::depth_im2col_kernel<14><<<B * Sd * (H / patch), 256, 0, st>>>(p);
-  else ovg::depth_im2col_kernel<0><<<B * Sd * (H / patch), 256, 0, st>>>(p);
+  if (rc || n_cols == 0) return rc;
+  ovg::DepthParams pc = ps;
+  pc.idx = idx_cols;
+  pc.Sd = n_cols;
+  if (patch == 14) ovg::depth_im2col_kernel<14><<<B * n_cols * (H / patch), 256, 0, st>>>(pc);
+  else ovg::depth_im2col_kernel<0><<<B * n_cols * (H / patch), 256, 0, st>>>(pc);
   return post_launch("ovg_depth_im2col");
+}
+
+int ovg_depth_im2col(const float* depth, const float* mask, const int* idx, double* scratch, void* cols, int ldc,
+                     int B, int S, int Sd, int H, int W, int patch, void* stream) {
+  OVG_REQUIRE(Sd > 0, "bad geometry");
+  return ovg_depth_im2col2(depth, mask, idx, Sd, idx, Sd, scratch, cols, ldc, B, S, H, W, patch, stream);
 }
 
 int ovg_image_im2col(const float* images, const float* mean3, const float* std3, void* cols, int ldc, int K, int H, int W,

@@ -324,11 +324,21 @@ class Engine:
         assert tuple(keep) == self.keep or set(keep) == set(self.keep), "kept layers are fixed when the engine is built"
         cos, sin = self.rope(max(hp, wp) + 1)
         Sd = len(depth_idx)
-        idx = d32 = m32 = None
+        idx = idx_loc = d32 = m32 = None
+        n_loc = 0
         if Sd:
+            # context parallel: depth / mask are the full [1, views_total, H, W] tensors, depth_idx the scene indices of all
+            # selected views (the normalisation mean is global), and the rank embeds only the selected views it owns
+            S_src = views_total if cp is not None else S
             idx = self.cached(("depth_idx", tuple(depth_idx)), lambda: torch.tensor(depth_idx, dtype=torch.int32))
-            d32 = depth.reshape(B, S, H, W).to(F32).contiguous()
-            m32 = mask.reshape(B, S, H, W).to(F32).contiguous()
+            d32 = depth.reshape(B, S_src, H, W).to(F32).contiguous()
+            m32 = mask.reshape(B, S_src, H, W).to(F32).contiguous()
+            if cp is not None:
+                v0, n = cp.local_views(views_total)
+                loc = [i for i in depth_idx if v0 <= i < v0 + n]
+                n_loc = len(loc)
+                if n_loc:
+                    idx_loc = self.cached(("depth_idx", tuple(loc)), lambda: torch.tensor(loc, dtype=torch.int32))
         wsb = self._workspace("agg_ws", lib.ovg_aggregator_workspace_bytes(self.h_agg, B, S, H, W, Sd))
         slot_t = [self.ws.get(f"slot{i}", (K, T, 2 * Cc)) for i in self.keep]
         slot_p = (C.c_void_p * 4)(*[t.data_ptr() for t in slot_t])
@@ -338,8 +348,9 @@ class Engine:
             assert B == 1, "context parallelism shards the views of one scene"
             cd = cp.desc(self.heads, views_total * T, views_total)
             L.check(lib.ovg_aggregator_forward_cp(self.h_agg, C.byref(cd), pt.data_ptr(), ij.data_ptr(), L.ptr(d32), L.ptr(m32),
-                                                  L.ptr(idx), Sd, cos.data_ptr(), sin.data_ptr(), cos.shape[0], S, H, W,
-                                                  wsb.data_ptr(), wsb.numel(), slot_p, cam_out.data_ptr(), L.stream()))
+                                                  L.ptr(idx), Sd, L.ptr(idx_loc), n_loc, cos.data_ptr(), sin.data_ptr(),
+                                                  cos.shape[0], S, H, W, wsb.data_ptr(), wsb.numel(), slot_p, cam_out.data_ptr(),
+                                                  L.stream()))
         else:
             L.check(lib.ovg_aggregator_forward(self.h_agg, pt.data_ptr(), ij.data_ptr(), L.ptr(d32), L.ptr(m32), L.ptr(idx), Sd,
                                                cos.data_ptr(), sin.data_ptr(), cos.shape[0], B, S, H, W, wsb.data_ptr(),

@@ -169,10 +169,8 @@ class OmniVGGT(nn.Module, PyTorchModelHubMixin):
             rows = eng.cached(("cam_rows", 1, S, tuple(cam_idx)), lambda: torch.tensor(cam_idx))
             pose = TP.aux_pose_encoding(extrinsics.index_select(1, ci), intrinsics.index_select(1, ci), H, W)
         inj = TP.injection_vectors(eng.inj_pack, pose, cam_idx, 1, S, rows)[:, sl].contiguous()
-        didx = cp.local_indices(depth_idx, S)
-        d_loc = depth[:, sl] if len(didx) else None
-        m_loc = mask[:, sl] if len(didx) else None
-        slots, cam_loc = eng.aggregate(patch, inj, d_loc, m_loc, didx, 1, n, H, W, set(self.dpt_layers), cp=cp, views_total=S)
+        # depth aux: full tensors + scene indices (the masked-mean normalisation is over all selected views of the scene)
+        slots, cam_loc = eng.aggregate(patch, inj, depth, mask, depth_idx, 1, n, H, W, set(self.dpt_layers), cp=cp, views_total=S)
         cam_all = cp.all_gather_rows(cam_loc)                       # [S, 2C]: the camera head attends across all views
         pose_list = self._camera(eng, cam_all, 1, S)
         eng.warm_tables(H, W)
