@@ -281,6 +281,8 @@ typedef struct ovg_context_parallel {
   void* v_peers[2][8];
   int* flag_peers[8];                 /* [rank]: int[world], peer mapped, zero-initialised once */
   int* epoch_counter;                 /* private device int, zero-initialised once */
+  float* cam_peers[8];                /* [rank]: fp32 [views_total, 2C] camera tokens of ALL views (the camera head attends across
+                                         views, heads/camera_head.py:104-154); every rank stores its rows into every peer */
 } ovg_context_parallel;
 /* As ovg_aggregator_forward with B = 1 and S = the LOCAL view count, except for the depth modality, whose normalisation is
  * global over the scene: depth / mask are the FULL tensors [1, views_total, H, W], depth_idx lists ALL selected views (scene
@@ -289,7 +291,7 @@ int ovg_aggregator_forward_cp(ovg_aggregator* h, const ovg_context_parallel* cp,
                               const float* depth, const float* mask, const int* depth_idx, int n_depth,
                               const int* depth_idx_local, int n_depth_local, const float* rope_cos, const float* rope_sin,
                               int maxpos, int S, int H, int W, void* workspace, long long workspace_bytes, void* const* slots,
-                              float* cam_out, void* stream);
+                              float* cam_out, void* stream);   /* cam_out: this rank's rows [S, 2C]; all views: cp->cam_peers[rank] */
 
 /* Timing hook for bench.py: when enabled, every global-attention launch of ovg_aggregator_forward is bracketed by CUDA events
  * on its stream; after a synchronize, ovg_runtime_attention_times() returns the elapsed ms of the launches since the enable. */

@@ -86,7 +86,7 @@ class CameraDesc(C.Structure):
 class ContextParallelDesc(C.Structure):
     """Mirror of ``ovg_context_parallel``."""
     _fields_ = [("rank", _i), ("world", _i), ("views_total", _i), ("k_peers", (_vp * 8) * 2), ("v_peers", (_vp * 8) * 2),
-                ("flag_peers", _vp * 8), ("epoch_counter", _vp)]
+                ("flag_peers", _vp * 8), ("epoch_counter", _vp), ("cam_peers", _vp * 8)]
 
 
 _pp = C.POINTER(_vp)

@@ -495,6 +495,21 @@ __global__ void __launch_bounds__(256) upsample_rows_kernel(const UpsampleParams
 // ---------------------------------------------------------------------------------------------------
 // Cross-GPU barrier on peer-mapped flags (context-parallel global attention): the K / V rows a rank stored into its peers'
 // buffers (QKV epilogue of the kernels before this one on the stream) become visible before any peer's attention reads them.
+// Rows of this rank -> the same row window of every peer's buffer (camera tokens of a sharded scene; a few KB).
+struct PeerRowsParams {
+  const float* src;     // [rows, width]
+  float* dst[8];        // per rank: [rows_total, width], peer mapped
+  int world, rows, width;
+  long long row_off;
+};
+__global__ void peer_rows_kernel(const PeerRowsParams p) {
+  const long long n4 = static_cast<long long>(p.rows) * p.width / 4;
+  float4* d = reinterpret_cast<float4*>(p.dst[blockIdx.y] + p.row_off * p.width);
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    d[i] = reinterpret_cast<const float4*>(p.src)[i];
+}
+
 struct PeerBarrierParams {
   int* flags[8];     // flags[r]: int[world] in rank r's memory (peer mapped)
   int* epoch;        // this rank's private barrier counter (device memory): every barrier uses the next value, so a captured

@@ -133,11 +133,10 @@ class OmniVGGT(nn.Module, PyTorchModelHubMixin):
             assert extrinsics is not None and intrinsics is not None, "camera_gt_index given without cameras"
         eng = self.engine()
         args = (images, extrinsics, intrinsics, depth, mask, depth_idx, cam_idx)
-        if self._cp is not None:
-            return self._forward_cp(eng, *args)
+        impl = self._forward_cp if self._cp is not None else self._forward_impl
         if self.use_cuda_graph and images.is_cuda and not torch.cuda.is_current_stream_capturing():
-            return self._forward_graphed(eng, *args)
-        return self._forward_impl(eng, *args)
+            return self._forward_graphed(eng, impl, *args)
+        return impl(eng, *args)
 
     # ---------------------------------------------------------------------------------------------- context parallelism
     def enable_context_parallel(self, group=None) -> "OmniVGGT":
@@ -171,8 +170,7 @@ class OmniVGGT(nn.Module, PyTorchModelHubMixin):
         inj = TP.injection_vectors(eng.inj_pack, pose, cam_idx, 1, S, rows)[:, sl].contiguous()
         # depth aux: full tensors + scene indices (the masked-mean normalisation is over all selected views of the scene)
         slots, cam_loc = eng.aggregate(patch, inj, depth, mask, depth_idx, 1, n, H, W, set(self.dpt_layers), cp=cp, views_total=S)
-        cam_all = cp.all_gather_rows(cam_loc)                       # [S, 2C]: the camera head attends across all views
-        pose_list = self._camera(eng, cam_all, 1, S)
+        pose_list = self._camera(eng, cp.cam_all, 1, S)            # [S, 2C] gathered by peer stores: the camera head attends across all views
         eng.warm_tables(H, W)
         d_out = eng.dpt("depth_head", slots, self.dpt_layers, n, H, W, head_act=0)
         p_out = eng.dpt("point_head", slots, self.dpt_layers, n, H, W, head_act=1)
@@ -205,14 +203,14 @@ class OmniVGGT(nn.Module, PyTorchModelHubMixin):
         return predictions
 
     # ---------------------------------------------------------------------------------------------- CUDA graph replay
-    def _forward_graphed(self, eng, images, extrinsics, intrinsics, depth, mask, depth_idx, cam_idx):
+    def _forward_graphed(self, eng, impl, images, extrinsics, intrinsics, depth, mask, depth_idx, cam_idx):
         """Same computation, launched from a captured CUDA graph (a forward is >1000 kernel launches; issuing them from
         Python costs about as much host time as the GPU needs to run them).  A graph is captured the third time a
         (shape, index-list) signature is seen; inputs are copied into static buffers, outputs are cloned."""
         need_c, need_d = len(cam_idx) > 0, len(depth_idx) > 0
         def sig(t):
             return None if t is None else (tuple(t.shape), t.dtype)
-        key = (sig(images), tuple(depth_idx), tuple(cam_idx), sig(extrinsics) if need_c else None,
+        key = (impl.__name__, sig(images), tuple(depth_idx), tuple(cam_idx), sig(extrinsics) if need_c else None,
                sig(intrinsics) if need_c else None, sig(depth) if need_d else None, sig(mask) if need_d else None)
         ent = self._graphs.pop(key, None)
         if ent is None:
@@ -222,7 +220,7 @@ class OmniVGGT(nn.Module, PyTorchModelHubMixin):
         self._graphs[key] = ent                             # most recently used last
         ent["calls"] += 1
         if ent["graph"] is None and (ent["calls"] < 3 or ent.get("failed")):
-            return self._forward_impl(eng, images, extrinsics, intrinsics, depth, mask, depth_idx, cam_idx)
+            return impl(eng, images, extrinsics, intrinsics, depth, mask, depth_idx, cam_idx)
         dyn = [images, extrinsics if need_c else None, intrinsics if need_c else None, depth if need_d else None,
                mask if need_d else None]
         if ent["graph"] is None or ent["ws_version"] != eng.ws.version:
@@ -231,11 +229,11 @@ class OmniVGGT(nn.Module, PyTorchModelHubMixin):
                 s = torch.cuda.Stream()
                 s.wait_stream(torch.cuda.current_stream())
                 with torch.cuda.stream(s):      # allocator warm-up on a side stream, as the capture API requires
-                    self._forward_impl(eng, *static, depth_idx, cam_idx)
+                    impl(eng, *static, depth_idx, cam_idx)
                 torch.cuda.current_stream().wait_stream(s)
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
-                    out = self._forward_impl(eng, *static, depth_idx, cam_idx)
+                    out = impl(eng, *static, depth_idx, cam_idx)
                 ent.update(graph=g, static=static, out=out, ws_version=eng.ws.version)
             except torch.cuda.OutOfMemoryError as ex:
                 # the only failure that is a property of the call, not a bug: the private pool of one more graph does not fit.
@@ -245,7 +243,7 @@ class OmniVGGT(nn.Module, PyTorchModelHubMixin):
                 warnings.warn(f"OmniVGGT: no memory for another CUDA graph ({ex}); this signature keeps eager launches")
                 torch.cuda.synchronize()
                 torch.cuda.empty_cache()
-                return self._forward_impl(eng, images, extrinsics, intrinsics, depth, mask, depth_idx, cam_idx)
+                return impl(eng, images, extrinsics, intrinsics, depth, mask, depth_idx, cam_idx)
         for st, t in zip(ent["static"], dyn):
             if st is not None:
                 st.copy_(t)
@@ -254,7 +252,7 @@ class OmniVGGT(nn.Module, PyTorchModelHubMixin):
         res = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in out.items() if k not in ("images", "pose_enc_list")}
         res["pose_enc_list"] = [t.clone() for t in out["pose_enc_list"]]
         res["pose_enc"] = res["pose_enc_list"][-1]
-        res["images"] = images
+        res["images"] = images if "view_range" not in out else images[:, out["view_range"][0]:out["view_range"][1]]
         return res
 
     def _camera(self, eng, cam_tokens, B, S):

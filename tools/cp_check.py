@@ -87,12 +87,22 @@ for k in ("depth", "depth_conf", "world_points", "world_points_conf"):
 same = torch.equal(out["pose_enc"], ref["pose_enc"])
 res["pose_enc"] = {"bit_identical": bool(same), "rel_l2": float((out["pose_enc"] - ref["pose_enc"]).norm() / ref["pose_enc"].norm())}
 ok &= res["pose_enc"]["rel_l2"] < 1e-6
+# the same under CUDA-graph replay (third call of a signature captures; a forward makes no collective call)
+m.use_cuda_graph = True
+for _ in range(3):
+    m(**kw)
+outg, ms_cpg = timed(lambda: m(**kw), args.steps if args.full else 2)
+res["ms_context_parallel_graph"] = ms_cpg
+res["graph_replay_bit_identical"] = bool(all(torch.equal(outg[k], ref[k][:, v0:v1]) for k in ("depth", "world_points")) and
+                                         torch.equal(outg["pose_enc"], ref["pose_enc"]))
+ok &= res["graph_replay_bit_identical"]
 res["ok"] = bool(ok)
 gathered = [None] * world
 dist.all_gather_object(gathered, res)
 if rank == 0:
     for r_ in gathered:
         print(json.dumps(r_))
-    print("CP_CHECK", "PASS" if all(r_["ok"] for r_ in gathered) else "FAIL", f"speedup {ms_single / ms_cp:.2f}x on {world} GPUs")
+    print("CP_CHECK", "PASS" if all(r_["ok"] for r_ in gathered) else "FAIL",
+          f"eager: single {ms_single:.2f} ms, cp {ms_cp:.2f} ms ({ms_single / ms_cp:.2f}x); cp graph replay {ms_cpg:.2f} ms on {world} GPUs")
 dist.destroy_process_group()
 sys.exit(0 if ok else 1)
