@@ -390,7 +390,7 @@ def main():
                        "weights": "random-init, full architecture (1217.5 M params)",
                        "l2": "no flush needed: each step streams >2 GB of weights+activations, far beyond the 126 MB L2",
                        "dino": "frozen DINOv2 patchifier on the libovg kernels",
-                       "launch": "eager (C++ runtime sequences)" if (args.cp or not model.use_cuda_graph) else "CUDA graph replay"},
+                       "launch": "CUDA graph replay" if model.use_cuda_graph else "eager (C++ runtime sequences)"},
             "clocks": clocks,
             "e2e": {"value": total_scenes * 1e3 / e2e_ms, "unit": "view-sets/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms},

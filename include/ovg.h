@@ -137,6 +137,26 @@ int ovg_im2col3x3s2(const void* src, void* dst, int F, int h, int w, int C, void
 int ovg_upsample_bilinear(const void* src, void* dst, const float* tx, const float* ty, int F, int h, int w, int H, int W,
                           int C, void* stream);
 
+/* GPU input pipeline: the per-view work of visual_util.py:719-841 (load_images_and_cameras) on
+ * decoded pixels.  The tap / index tables are small per-image-size arrays computed by the host with the libraries' own arithmetic
+ * (Pillow Resample.c precompute_coeffs + normalize_coeffs_8bpc; OpenCV resizeNN).
+ * ovg_preprocess_image: uint8 RGB [h, w, 3] -> Pillow-exact bicubic resize to [nh, nw] (two passes, uint8 rounding after each) ->
+ * rows [crop, crop + fh) -> fp32 [3, fh, nw] = uint8 / 255 (ToTensor).  (hmin, hcnt, hk[nw, hksize]) / (vmin, vcnt, vk[nh, vksize]):
+ * first source index, tap count and 22-bit fixed-point taps per output column / row; an axis that keeps its size passes NULLs.
+ * tmp: uint8 [h, nw, 3] scratch (unused when w == nw).   visual_util.py:731-751 */
+int ovg_preprocess_image(const unsigned char* src, int h, int w, int nw, int nh, int crop, int fh, const int* hmin, const int* hcnt,
+                         const int* hk, int hksize, const int* vmin, const int* vcnt, const int* vk, int vksize,
+                         unsigned char* tmp, float* out, void* stream);
+/* ovg_preprocess_depth: validity filter (non-finite, > max_depth, < 1e-5 -> 0) + nearest-neighbour resize through the index tables
+ * sy[nh], sx[nw] + crop -> depth fp32 [fh, nw], mask fp32 [fh, nw] (depth > 1e-5).  src element (r, c) at
+ * src[r * row_stride + c * col_stride] (the reference transposes PNG depth maps: swap the strides).   visual_util.py:768-791 */
+int ovg_preprocess_depth(const float* src, long long row_stride, long long col_stride, const int* sy, const int* sx, int crop,
+                         int fh, int nw, float max_depth, float* depth, float* mask, void* stream);
+/* ovg_prepare_cameras: camera-to-world [K,3,4] -> world-to-camera (closed-form SE3 inverse); intrinsics [K,3,3] rescaled by
+ * geom[k] = (scale_x, scale_y, crop_y or < 0) ; views with has[k] == 0 get the reference's zero placeholders.  visual_util.py:807-824 */
+int ovg_prepare_cameras(const float* c2w, const float* kin, const float* geom, const int* has, float* w2c, float* kout, int K,
+                        void* stream);
+
 /* On-device post-processing: what inference.py does on the host right after the forward.
  * ovg_pose_decode: pose_enc fp32 [K,9] = [t, quat xyzw, fov_h, fov_w] -> extrinsic [K,3,4] (world->camera, [R|t]),
  * intrinsic [K,3,3] (fx = (W/2)/tan(fov_w/2), fy = (H/2)/tan(fov_h/2), principal point at the image centre; may be NULL) and

@@ -622,8 +622,7 @@ constexpr int HT_B_BYTES = 18 * HT_B_TILE;           // 9 taps x 2 K blocks
 constexpr int HT_SMEM_BYTES = HT_STAGES * HT_A_BYTES + HT_B_BYTES + 1024 + 256;
 
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-headtail_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p,
-                const int use_base_offset) {
+headtail_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
@@ -704,7 +703,7 @@ headtail_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             const uint32_t a_atom = smem_u32(sA + s * HT_A_BYTES);
 #pragma unroll
             for (int kx = 0; kx < 3; ++kx) {
-              const uint64_t adesc = make_sw128_desc_rows(a_atom, kx, use_base_offset);
+              const uint64_t adesc = make_sw128_desc_rows(a_atom, kx);
               const uint64_t bdesc = make_sw128_desc(smem_u32(sB + ((ky * 3 + kx) * 2 + kb) * HT_B_TILE));
 #pragma unroll
               for (int k = 0; k < GEMM_BK / 16; ++k)

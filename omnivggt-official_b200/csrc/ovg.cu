@@ -14,14 +14,12 @@
 #include "elem.cuh"
 #include "gemm.cuh"
 #include "post.cuh"
+#include "pre.cuh"
 
 namespace {
 
 thread_local std::string g_err;
 std::atomic<long long> g_launches{0};
-const bool g_stage_default = [] { const char* e = getenv("OVG_GEMM_STAGE"); return !(e && e[0] == '0'); }();   // A/B switch
-const bool g_split_default = [] { const char* e = getenv("OVG_GEMM_SPLIT"); return !(e && e[0] == '0'); }();   // A/B switch
-const bool g_pair_default = [] { const char* e = getenv("OVG_GEMM_PAIR"); return !(e && e[0] == '0'); }();   // A/B switch
 
 int fail(int code, const std::string& msg) {
   g_err = msg;
@@ -200,7 +198,7 @@ int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap
   const int grid = 2 * (tiles < pairs ? tiles : pairs);
   // last partial wave as half tiles when both halves of every leftover tile find a free cluster (gemm.cuh)
   const int tail = tiles > pairs ? tiles % pairs : 0;
-  p.split_tail = (BN == 256 && g_split_default && tail > 0 && 2 * tail <= pairs) ? 1 : 0;
+  p.split_tail = (BN == 256 && tail > 0 && 2 * tail <= pairs) ? 1 : 0;
   kern<<<grid, ovg::GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, tbh, to[0], to[1], to[2], p);
   return post_launch("ovg_gemm(2sm)");
 }
@@ -351,7 +349,7 @@ int ovg_gemm(const ovg_gemm_args* a, void* stream) {
   // block_n 512 / 384 select the CTA-pair kernels (256 x 256 / 256 x 128 tile per 2-SM cluster).  They stage 33% fewer
   // L2->SM bytes per FLOP than the single-CTA tiles, which is what bounds these GEMMs; auto-selected for large problems.
   const bool pair = (a->block_n == 512 || a->block_n == 384) ||
-                    (a->block_n == 0 && g_pair_default && a->epi != OVG_EPI_HEADTAIL && a->n >= 128 && a->m >= 1024);
+                    (a->block_n == 0 && a->epi != OVG_EPI_HEADTAIL && a->n >= 128 && a->m >= 1024);
   if (pair) {
     OVG_REQUIRE(a->epi != OVG_EPI_HEADTAIL, "pair kernel has no HEADTAIL epilogue");
     const int pbn = (a->block_n == 384 || (a->block_n == 0 && a->n < 256)) ? 128 : 256;
@@ -369,7 +367,7 @@ int ovg_gemm(const ovg_gemm_args* a, void* stream) {
       rc = get_out_map(a->out, a->epi == OVG_EPI_RESID, a->n, a->m, a->ldo, &to[0]);
       if (rc) return rc;
       p.staged = 1;
-    } else if (g_stage_default && a->epi == OVG_EPI_QKV && a->n_peers == 0) {
+    } else if (a->epi == OVG_EPI_QKV && a->n_peers == 0) {
       // head-major q / k / v [batch * heads, ntok, 64]: one 32-token x 64 box per bulk store
       const unsigned long long bh = static_cast<unsigned long long>(a->m / a->ntok) * (a->C / 64);
       const void* outs[3] = {a->q_out, a->k_out, a->v_out};
@@ -403,8 +401,7 @@ int ovg_gemm(const ovg_gemm_args* a, void* stream) {
     case OVG_EPI_QKV: return dispatch_bn<ovg::EPI_QKV>(bn, ta, tb, p, st);
     case OVG_EPI_HEADTAIL: {
       // row-shift kernel: 3x3 taps in row-major order over a 128-channel map ((ky, kx) -> tap_off = (ky-1)*pitch + kx-1)
-      static const int ht_mode = [] { const char* e = getenv("OVG_HT_ROWSHIFT"); return e ? atoi(e) : 1; }();   // 0: generic 9-tap path; 1: row-shifted descriptors; 2: + base-offset field (wrong on sm_100, kept for the record)
-      bool shape_ok = ht_mode > 0 && a->num_taps == 9 && a->a_cols == 128 && a->n == 32;
+      bool shape_ok = a->num_taps == 9 && a->a_cols == 128 && a->n == 32;
       for (int ky = 0; ky < 3 && shape_ok; ++ky)
         shape_ok = a->tap_off[ky * 3 + 1] - a->tap_off[ky * 3] == 1 && a->tap_off[ky * 3 + 2] - a->tap_off[ky * 3 + 1] == 1;
       if (!shape_ok) return launch_gemm<32, ovg::EPI_HEADTAIL>(ta, tb, p, st);
@@ -420,7 +417,7 @@ int ovg_gemm(const ovg_gemm_args* a, void* stream) {
       }
       const int tiles = (p.M + ovg::GEMM_BM - 1) / ovg::GEMM_BM;
       const int grid = tiles < num_sms() ? tiles : num_sms();
-      ovg::headtail_kernel<<<grid, ovg::GEMM_THREADS, ovg::HT_SMEM_BYTES, st>>>(ta136, tb32, p, ht_mode == 2 ? 1 : 0);
+      ovg::headtail_kernel<<<grid, ovg::GEMM_THREADS, ovg::HT_SMEM_BYTES, st>>>(ta136, tb32, p);
       return post_launch("ovg_gemm(headtail)");
     }
     default: return fail(OVG_E_INVALID, "ovg_gemm: unknown epilogue");
@@ -464,12 +461,12 @@ int ovg_layernorm(const void* in, int in_is_bf16, long long ld_in, void* out, in
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   ovg::LnParams p{in, in_is_bf16, ld_in, out, out_is_f32, ld_out, rows, C, w, b, eps,
                   grp_out, grp_in, grp_off};
-  static const int ln_threads = [] { const char* e = getenv("OVG_LN_THREADS"); return e ? atoi(e) : 256; }();   // A/B switch
-  static const int ln_persist = [] { const char* e = getenv("OVG_LN_PERSIST"); return e ? atoi(e) : 2; }();     // blocks per SM (0: one row per warp)
+  constexpr int ln_threads = 256;     // 8 rows per block
+  constexpr int ln_persist = 2;       // persistent grid: blocks per SM
   OVG_REQUIRE((reinterpret_cast<uintptr_t>(w) & 15) == 0 && (reinterpret_cast<uintptr_t>(b) & 15) == 0, "w / b must be 16-byte aligned");
   const int rpb = ln_threads / 32;
   int blocks = (rows + rpb - 1) / rpb;
-  if (ln_persist > 0 && blocks > 148 * ln_persist) blocks = 148 * ln_persist;
+  if (blocks > num_sms() * ln_persist) blocks = num_sms() * ln_persist;
   switch (C / 32) {
 #define OVG_LN_CASE(V) \
   case V: ovg::layernorm_kernel<V><<<blocks, ln_threads, 0, st>>>(p); break;
@@ -579,9 +576,8 @@ int ovg_upsample_bilinear(const void* src, void* dst, const float* tx, const flo
                         F, h, w, H, W, C,
                         H > 1 ? static_cast<float>(h - 1) / static_cast<float>(H - 1) : 0.f,
                         W > 1 ? static_cast<float>(w - 1) / static_cast<float>(W - 1) : 0.f};
-  static const int rows_kernel = [] { const char* e = getenv("OVG_UPSAMPLE_ROWS"); return e ? atoi(e) : 1; }();   // A/B switch
   const size_t row_smem = static_cast<size_t>(w) * 32 * sizeof(float);
-  if (rows_kernel && C % 32 == 0 && row_smem <= 48 * 1024 && C / 32 <= 65535) {
+  if (C % 32 == 0 && row_smem <= 48 * 1024 && C / 32 <= 65535) {
     dim3 grid(H + 2, F, C / 32);
     ovg::upsample_rows_kernel<<<grid, 256, row_smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
     return post_launch("ovg_upsample_bilinear");
@@ -590,6 +586,43 @@ int ovg_upsample_bilinear(const void* src, void* dst, const float* tx, const flo
   dim3 grid((per_row + 255) / 256, H + 2, F);
   ovg::upsample_bilinear_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
   return post_launch("ovg_upsample_bilinear");
+}
+
+int ovg_preprocess_image(const unsigned char* src, int h, int w, int nw, int nh, int crop, int fh, const int* hmin, const int* hcnt,
+                         const int* hk, int hksize, const int* vmin, const int* vcnt, const int* vk, int vksize,
+                         unsigned char* tmp, float* out, void* stream) {
+  OVG_REQUIRE(src && out && h > 0 && w > 0 && nw > 0 && nh > 0 && crop >= 0 && fh > 0 && crop + fh <= nh, "bad geometry");
+  OVG_REQUIRE(w == nw || (hmin && hcnt && hk && hksize > 0 && tmp), "horizontal pass needs its tap table and a temporary");
+  OVG_REQUIRE(h == nh || (vmin && vcnt && vk && vksize > 0), "vertical pass needs its tap table");
+  OVG_REQUIRE(h <= 65535 && fh <= 65535, "image too tall");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const unsigned char* mid = src;
+  if (w != nw) {
+    ovg::ResizeParams ph{src, tmp, nullptr, hmin, hcnt, hk, hksize, h, w, nw, 0, 0, 0};
+    ovg::resize_h_u8_kernel<<<dim3((nw + 127) / 128, h), 128, 0, st>>>(ph);
+    int rc = post_launch("ovg_preprocess_image(horizontal)");
+    if (rc) return rc;
+    mid = tmp;
+  }
+  ovg::ResizeParams pv{mid, nullptr, out, vmin, vcnt, vk, vksize, h, w, nw, crop, fh, h == nh ? 1 : 0};
+  ovg::resize_v_u8_f32_kernel<<<dim3((nw + 127) / 128, fh), 128, 0, st>>>(pv);
+  return post_launch("ovg_preprocess_image");
+}
+
+int ovg_preprocess_depth(const float* src, long long row_stride, long long col_stride, const int* sy, const int* sx, int crop,
+                         int fh, int nw, float max_depth, float* depth, float* mask, void* stream) {
+  OVG_REQUIRE(src && sy && sx && depth && mask && fh > 0 && nw > 0 && crop >= 0 && fh <= 65535, "bad arguments");
+  ovg::DepthNearestParams p{src, row_stride, col_stride, sy, sx, depth, mask, crop, fh, nw, max_depth};
+  ovg::depth_nearest_kernel<<<dim3((nw + 255) / 256, fh), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  return post_launch("ovg_preprocess_depth");
+}
+
+int ovg_prepare_cameras(const float* c2w, const float* kin, const float* geom, const int* has, float* w2c, float* kout, int K,
+                        void* stream) {
+  OVG_REQUIRE(c2w && kin && geom && has && w2c && kout && K > 0, "bad arguments");
+  ovg::CameraPrepParams p{c2w, kin, geom, has, w2c, kout, K};
+  ovg::camera_prepare_kernel<<<(K + 63) / 64, 64, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  return post_launch("ovg_prepare_cameras");
 }
 
 int ovg_pose_decode(const float* pose_enc, float* extrinsic, float* intrinsic, float* cam2world, int K, int H, int W,

@@ -240,12 +240,9 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
 }
 // Same, for a matrix that starts `row_off` (0..7) 128-byte rows into a 1024-byte swizzle atom.  Measured on sm_100
 // (tests/test_kernels_gpu.py::test_head_tail): the unit applies the 128B swizzle to ABSOLUTE shared-memory address bits,
-// so advancing the start address by whole rows is all it takes; setting the base-offset field (bits 49-51) to the row
-// phase gives wrong results.
-__device__ __forceinline__ uint64_t make_sw128_desc_rows(uint32_t saddr_atom, int row_off, int use_base_offset) {
-  uint64_t d = make_sw128_desc(saddr_atom + static_cast<uint32_t>(row_off) * 128u);
-  if (use_base_offset) d |= static_cast<uint64_t>(row_off & 7) << 49;
-  return d;
+// so advancing the start address by whole rows is all it takes (the descriptor's base-offset field stays 0).
+__device__ __forceinline__ uint64_t make_sw128_desc_rows(uint32_t saddr_atom, int row_off) {
+  return make_sw128_desc(saddr_atom + static_cast<uint32_t>(row_off) * 128u);
 }
 // kind::f16 instruction descriptor: bf16 x bf16 -> fp32.
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn_major, int b_mn_major) {

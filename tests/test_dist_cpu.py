@@ -54,3 +54,37 @@ def test_broadcast_and_sharding_world2():
     assert res[0][4] == [0, 2, 4, 6] and res[1][4] == [1, 3, 5]
     assert sorted(res[0][4] + res[1][4]) == list(range(7))
     assert res[0][5] == res[1][5] == 2.0
+
+
+def _cp_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from omnivggt_official_b200.context_parallel import ContextParallel
+    cp = ContextParallel(torch.device("cpu"))
+    out = (rank, cp.rank, cp.world, cp.local_views(8), cp.local_indices([0, 3, 4, 7], 8), cp.local_indices([], 8))
+    try:
+        cp.local_views(7)
+        out += (False,)
+    except ValueError:
+        out += (True,)
+    q.put(out)
+    dist.destroy_process_group()
+
+
+def test_context_parallel_view_partition_world2():
+    """Host logic of the context-parallel path (the K / V exchange itself needs peer-mapped GPU memory: tools/cp_check.py,
+    tests/test_cp_gpu.py): contiguous, equal view windows in rank order; index lists filtered to the owned views."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    ps = [ctx.Process(target=_cp_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in ps:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in ps:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert [r[3] for r in res] == [(0, 4), (4, 4)] and [r[2] for r in res] == [2, 2]
+    assert res[0][4] == [0, 3] and res[1][4] == [0, 3]          # scene indices [0,3] / [4,7] relative to the window start
+    assert res[0][5] == [] and all(r[6] for r in res)            # 7 views cannot be split over 2 ranks
