@@ -360,9 +360,8 @@ int ovg_gemm(const ovg_gemm_args* a, void* stream) {
     if (rc) return rc;
     // staged epilogue (smem -> TMA store / fp32 reduce-add) whenever output rows are the GEMM rows
     CUtensorMap to[3] = {ta, ta, ta};
-    const bool stage_ok = g_stage_default &&
-                          ((a->epi == OVG_EPI_RESID && !a->row_index) ||
-                           (a->epi == OVG_EPI_BF16 && (a->rowmap == OVG_ROWS_IDENT || a->rowmap == OVG_ROWS_PAD)));
+    const bool stage_ok = (a->epi == OVG_EPI_RESID && !a->row_index) ||
+                          (a->epi == OVG_EPI_BF16 && (a->rowmap == OVG_ROWS_IDENT || a->rowmap == OVG_ROWS_PAD));
     if (stage_ok) {
       rc = get_out_map(a->out, a->epi == OVG_EPI_RESID, a->n, a->m, a->ldo, &to[0]);
       if (rc) return rc;

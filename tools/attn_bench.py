@@ -34,7 +34,7 @@ def timeit(fn, iters=7, warm=2):
 
 
 res = {"tag": sys.argv[1] if len(sys.argv) > 1 else "", "lib": os.environ.get("OVG_LIB_PATH", "libovg.so"),
-       "kernel": os.environ.get("OVG_ATTN_KERNEL", "3")}
+       }
 shapes = {"global8": (1, 16, 8 * 1374), "frame8": (8, 16, 1374), "global24": (1, 16, 24 * 1374)}
 if os.environ.get("ATTN_SHAPES"):
     shapes = {k: shapes[k] for k in os.environ["ATTN_SHAPES"].split(",")}
