@@ -438,3 +438,63 @@ def test_c_host_drives_the_runtime(tmp_path):
     print(r.stdout, r.stderr)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "0 mismatches" in r.stdout
+
+
+# ----------------------------------------------------------------------------------------------- context-parallel pieces (one GPU)
+def test_attention_kv_own_queries_against_all_keys():
+    """ovg_attention_kv: a window of the query rows against ALL keys equals the same rows of the full self-attention bit for bit
+    (what a rank of the context-parallel global block computes)."""
+    ops = _ops()
+    heads, n, lo, hi = 4, 1374 * 2, 1374, 1374 + 700
+    q = randn(1, heads, n, 64, seed=1, dtype=BF16) * 0.18
+    k = randn(1, heads, n, 64, seed=2, dtype=BF16)
+    v = randn(1, heads, n, 64, seed=3, dtype=BF16)
+    full = torch.zeros(1, n, heads * 64, device="cuda", dtype=BF16)
+    ops.attention(q, k, v, full, 1, heads, n)
+    part = torch.zeros(1, hi - lo, heads * 64, device="cuda", dtype=BF16)
+    ops.attention_kv(q[:, :, lo:hi].contiguous(), k, v, part, 1, heads, hi - lo, n)
+    torch.cuda.synchronize()
+    assert torch.equal(part, full[:, lo:hi])
+
+
+def test_qkv_epilogue_stores_kv_rows_into_peer_buffers():
+    """EPI_QKV with k_peers / v_peers: the K / V rows of this rank's tokens land in every listed full-length buffer at the rank's
+    token offset (here both "peers" are local allocations) and equal what the plain epilogue writes; q stays local."""
+    ops = _ops()
+    C, T, frames, hp, wp = 256, 25, 2, 4, 5
+    heads, M = C // 64, frames * T
+    a = randn(M, C, seed=1, dtype=BF16)
+    w = randn(3 * C, C, scale=C ** -0.5, seed=2, dtype=BF16)
+    bias = randn(3 * C, scale=0.1, seed=3)
+    ln = [1 + 0.1 * randn(64, seed=4), 0.1 * randn(64, seed=5), 1 + 0.1 * randn(64, seed=6), 0.1 * randn(64, seed=7)]
+    cos, sin = ops.rope_tables(max(hp, wp) + 1, "cuda")
+    q0, k0, v0 = (torch.zeros(1, heads, M, 64, device="cuda", dtype=BF16) for _ in range(3))
+    ops.qkv_proj(a, w, bias, *ln, q0, k0, v0, ntok=M, T=T, nspecial=5, wp=wp, rope_cos=cos, rope_sin=sin)
+    total, off = 3 * M, M                       # this "rank" owns tokens [M, 2M) of a 3M-token scene
+    peers_k = [torch.full((1, heads, total, 64), 7.0, device="cuda", dtype=BF16) for _ in range(2)]
+    peers_v = [torch.full((1, heads, total, 64), 7.0, device="cuda", dtype=BF16) for _ in range(2)]
+    q1 = torch.zeros_like(q0)
+    import ctypes
+    kp = (ctypes.c_void_p * 8)(*[t.data_ptr() for t in peers_k])
+    vp = (ctypes.c_void_p * 8)(*[t.data_ptr() for t in peers_v])
+    ops.gemm(a, w, epi=ops.L.EPI_QKV, bias=bias, q_out=q1, k_out=None, v_out=None, C=C, ntok=M, T=T, nspecial=5, wp=wp,
+             maxpos=cos.shape[0], qn_w=ln[0], qn_b=ln[1], kn_w=ln[2], kn_b=ln[3], rope_cos=cos, rope_sin=sin, qk_norm=1, rope=1,
+             qscale=(1.0 / math.sqrt(64.0)) * math.log2(math.e), k_peers=kp, v_peers=vp, n_peers=2, peer_ntok=total, peer_tok_off=off)
+    torch.cuda.synchronize()
+    assert torch.equal(q1, q0)
+    for pk, pv in zip(peers_k, peers_v):
+        assert torch.equal(pk[:, :, off:off + M], k0) and torch.equal(pv[:, :, off:off + M], v0)
+        assert (pk[:, :, :off] == 7.0).all() and (pk[:, :, off + M:] == 7.0).all() and (pv[:, :, :off] == 7.0).all()
+
+
+def test_peer_barrier_single_rank_and_epoch():
+    """The flag barrier with world = 1 must pass immediately and bump the device epoch once per call (graph-replay safe)."""
+    from omnivggt_official_b200 import _lib as L
+    import ctypes
+    flags = torch.zeros(8, dtype=torch.int32, device="cuda")
+    epoch = torch.zeros(1, dtype=torch.int32, device="cuda")
+    fp = (ctypes.c_void_p * 8)(flags.data_ptr())
+    for _ in range(3):
+        L.check(L.lib().ovg_peer_barrier(fp, epoch.data_ptr(), 0, 1, L.stream()))
+    torch.cuda.synchronize()
+    assert int(epoch.item()) == 3 and int(flags[0].item()) == 3
