@@ -81,6 +81,10 @@ typedef struct ovg_gemm_args {
    * k_out / v_out are then unused.  The exchange of models/aggregator.py:312-341's single SDPA over all views is thereby
    * fused into the producing GEMM's epilogue. */
   void* k_peers[8]; void* v_peers[8]; int n_peers; int peer_ntok; long long peer_tok_off;
+  /* OVG_EPI_BF16 / OVG_EPI_HEADTAIL: a, b, skip1, skip2 and the 16-bit output are IEEE half (fp16) instead of bf16 -- same tensor-core
+   * rate, 3 more mantissa bits; stores saturate to +-65504.  Used by the DPT heads, which the reference keeps in fp32 even under
+   * autocast (models/omnivggt.py:45). */
+  int f16;
 } ovg_gemm_args;
 
 int ovg_gemm(const ovg_gemm_args* args, void* stream);
@@ -94,7 +98,7 @@ int ovg_attention(const void* q, const void* k, const void* v, void* out, int ba
 int ovg_attention_kv(const void* q, const void* k, const void* v, void* out, int batch, int heads, int nq, int nkv,
                      void* stream);
 
-/* LayerNorm over the last dim, fp32 or bf16 in -> bf16 (or fp32) out, optional affine, optional row gather
+/* LayerNorm over the last dim, fp32 or bf16 in -> bf16 (out_is_f32 = 0), fp32 (1) or fp16 (2) out, optional affine, optional row gather
  * (out row m <- in row (m / grp_out) * grp_in + grp_off + m % grp_out; grp_out = 0: identity).
  * layers/block.py:50,:67 (eps 1e-5); heads/dpt_head.py:66,:219-227. */
 int ovg_layernorm(const void* in, int in_is_bf16, long long ld_in, void* out, int out_is_f32, long long ld_out, int rows,
@@ -131,11 +135,11 @@ int ovg_image_im2col(const float* images, const float* mean3, const float* std3,
 /* im2col for the stride-2 3x3 conv (heads/dpt_head.py:93-95): bf16 NHWC [F,h,w,C] -> [F*oh*ow, 9*C]. */
 int ovg_im2col3x3s2(const void* src, void* dst, int F, int h, int w, int C, void* stream);
 
-/* Bilinear align_corners=True upsampling between zero-bordered bf16 NHWC maps (heads/dpt_head.py:242-247,:466,
- * :472-497) with the optional UV position embedding of heads/dpt_head.py:249-250 given in separable form: tx fp32
- * [W, C/2] for channels [0, C/2), ty fp32 [H, C/2] for channels [C/2, C) (both NULL: no embedding). */
+/* Bilinear align_corners=True upsampling between zero-bordered bf16 (f16 = 0) or fp16 (f16 = 1) NHWC maps
+ * (heads/dpt_head.py:242-247,:466,:472-497) with the optional UV position embedding of heads/dpt_head.py:249-250 given in
+ * separable form: tx fp32 [W, C/2] for channels [0, C/2), ty fp32 [H, C/2] for channels [C/2, C) (both NULL: no embedding). */
 int ovg_upsample_bilinear(const void* src, void* dst, const float* tx, const float* ty, int F, int h, int w, int H, int W,
-                          int C, void* stream);
+                          int C, int f16, void* stream);
 
 /* GPU input pipeline: the per-view work of visual_util.py:719-841 (load_images_and_cameras) on
  * decoded pixels.  The tap / index tables are small per-image-size arrays computed by the host with the libraries' own arithmetic
@@ -248,6 +252,8 @@ typedef struct ovg_dpt_desc {
   const void* oc1_w; const float* oc1_b;                      /* output_conv1 3x3 feat -> feat/2 */
   const void* oc2_w; const float* oc2_b;                      /* output_conv2[0] 3x3 feat/2 -> 32 */
   const float* w2; const float* b2;                           /* output_conv2[2] 1x1 32 -> outc (fp32) */
+  int f16;                                                    /* 1: every 16-bit weight above and every intermediate map is fp16
+                                                                 (11-bit significand, saturating stores) instead of bf16 */
 } ovg_dpt_desc;
 typedef struct ovg_dpt ovg_dpt;
 int ovg_dpt_create(const ovg_dpt_desc* desc, ovg_dpt** out);

@@ -22,7 +22,7 @@ struct LnParams {
   int in_bf16;
   long long ld_in;
   void* out;
-  int out_f32;
+  int out_f32;      // output type: 0 bf16, 1 fp32, 2 IEEE half (saturating)
   long long ld_out;
   int rows, C;
   const float* w;
@@ -102,13 +102,13 @@ __global__ void __launch_bounds__(256, 2) layernorm_kernel(const LnParams p) {
         o[2] = fmaf(o[2], w4.z, b4.z);
         o[3] = fmaf(o[3], w4.w, b4.w);
       }
-      if (p.out_f32) {
+      if (p.out_f32 == 1) {
         *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + static_cast<long long>(row) * p.ld_out + c) =
             make_float4(o[0], o[1], o[2], o[3]);
       } else {
         uint2 u;
-        u.x = pack_bf16(o[0], o[1]);
-        u.y = pack_bf16(o[2], o[3]);
+        u.x = pack_h(o[0], o[1], p.out_f32 == 2);
+        u.y = pack_h(o[2], o[3], p.out_f32 == 2);
         *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<long long>(row) * p.ld_out + c) = u;
       }
     }
@@ -375,6 +375,7 @@ struct UpsampleParams {
   const float* ty;
   int F, h, w, H, W, C;
   float sy, sx;
+  int f16;          // maps are IEEE half instead of bf16
 };
 
 __global__ void __launch_bounds__(256) upsample_bilinear_kernel(const UpsampleParams p) {
@@ -402,8 +403,9 @@ __global__ void __launch_bounds__(256) upsample_bilinear_kernel(const UpsamplePa
     float r[8];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      r[2 * i] = wy0 * (wx0 * bf16_lo(ap[i]) + wx1 * bf16_lo(bp[i])) + wy1 * (wx0 * bf16_lo(cp[i]) + wx1 * bf16_lo(dp[i]));
-      r[2 * i + 1] = wy0 * (wx0 * bf16_hi(ap[i]) + wx1 * bf16_hi(bp[i])) + wy1 * (wx0 * bf16_hi(cp[i]) + wx1 * bf16_hi(dp[i]));
+      const float2 va = unpack_h(ap[i], p.f16), vb = unpack_h(bp[i], p.f16), vc = unpack_h(cp[i], p.f16), vd = unpack_h(dp[i], p.f16);
+      r[2 * i] = wy0 * (wx0 * va.x + wx1 * vb.x) + wy1 * (wx0 * vc.x + wx1 * vd.x);
+      r[2 * i + 1] = wy0 * (wx0 * va.y + wx1 * vb.y) + wy1 * (wx0 * vc.y + wx1 * vd.y);
     }
     if (p.tx) {
       const int half = p.C >> 1;
@@ -413,10 +415,10 @@ __global__ void __launch_bounds__(256) upsample_bilinear_kernel(const UpsamplePa
       r[0] += t0.x; r[1] += t0.y; r[2] += t0.z; r[3] += t0.w;
       r[4] += t1.x; r[5] += t1.y; r[6] += t1.z; r[7] += t1.w;
     }
-    out.x = pack_bf16(r[0], r[1]);
-    out.y = pack_bf16(r[2], r[3]);
-    out.z = pack_bf16(r[4], r[5]);
-    out.w = pack_bf16(r[6], r[7]);
+    out.x = pack_h(r[0], r[1], p.f16);
+    out.y = pack_h(r[2], r[3], p.f16);
+    out.z = pack_h(r[4], r[5], p.f16);
+    out.w = pack_h(r[6], r[7], p.f16);
   }
   *(reinterpret_cast<uint4*>(p.dst + (static_cast<size_t>(f) * (p.H + 2) * (p.W + 2) + static_cast<size_t>(Y) * (p.W + 2) + X) * p.C) + cv) = out;
 }
@@ -453,8 +455,9 @@ __global__ void __launch_bounds__(256) upsample_rows_kernel(const UpsampleParams
     float r[8];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      r[2 * k] = wy0 * bf16_lo(ap[k]) + wy1 * bf16_lo(bp[k]);
-      r[2 * k + 1] = wy0 * bf16_hi(ap[k]) + wy1 * bf16_hi(bp[k]);
+      const float2 va = unpack_h(ap[k], p.f16), vb = unpack_h(bp[k], p.f16);
+      r[2 * k] = wy0 * va.x + wy1 * vb.x;
+      r[2 * k + 1] = wy0 * va.y + wy1 * vb.y;
     }
     float4* d = reinterpret_cast<float4*>(srow + x * 32 + v * 8);
     d[0] = make_float4(r[0], r[1], r[2], r[3]);
@@ -483,10 +486,10 @@ __global__ void __launch_bounds__(256) upsample_rows_kernel(const UpsampleParams
         r[0] += t0.x; r[1] += t0.y; r[2] += t0.z; r[3] += t0.w;
         r[4] += t1.x; r[5] += t1.y; r[6] += t1.z; r[7] += t1.w;
       }
-      out.x = pack_bf16(r[0], r[1]);
-      out.y = pack_bf16(r[2], r[3]);
-      out.z = pack_bf16(r[4], r[5]);
-      out.w = pack_bf16(r[6], r[7]);
+      out.x = pack_h(r[0], r[1], p.f16);
+      out.y = pack_h(r[2], r[3], p.f16);
+      out.z = pack_h(r[4], r[5], p.f16);
+      out.w = pack_h(r[6], r[7], p.f16);
     }
     *reinterpret_cast<uint4*>(drow + static_cast<size_t>(X) * p.C + v * 8) = out;
   }

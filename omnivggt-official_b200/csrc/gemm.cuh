@@ -30,6 +30,7 @@ struct GemmParams {
   // ---- EPI_BF16
   const float* table;  // additive fp32 [table_rows][N] indexed by (m % table_rows), or nullptr
   int table_rows;
+  int f16;                     // EPI_BF16 / EPI_HEADTAIL: operands, skips and the 16-bit output are IEEE half instead of bf16
   const __nv_bfloat16* skip1;  // optional addends, indexed like `out`
   const __nv_bfloat16* skip2;
   int rowmap;  // RowMap
@@ -383,10 +384,11 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const uint32_
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const uint4 sv = __ldg(s4 + i);
-            v[8 * i + 0] += bf16_lo(sv.x); v[8 * i + 1] += bf16_hi(sv.x);
-            v[8 * i + 2] += bf16_lo(sv.y); v[8 * i + 3] += bf16_hi(sv.y);
-            v[8 * i + 4] += bf16_lo(sv.z); v[8 * i + 5] += bf16_hi(sv.z);
-            v[8 * i + 6] += bf16_lo(sv.w); v[8 * i + 7] += bf16_hi(sv.w);
+            const float2 s0 = unpack_h(sv.x, p.f16), s1 = unpack_h(sv.y, p.f16), s2 = unpack_h(sv.z, p.f16), s3 = unpack_h(sv.w, p.f16);
+            v[8 * i + 0] += s0.x; v[8 * i + 1] += s0.y;
+            v[8 * i + 2] += s1.x; v[8 * i + 3] += s1.y;
+            v[8 * i + 4] += s2.x; v[8 * i + 5] += s2.y;
+            v[8 * i + 6] += s3.x; v[8 * i + 7] += s3.y;
           }
         }
         if (p.skip2 && row_ok) {
@@ -394,10 +396,11 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const uint32_
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const uint4 sv = __ldg(s4 + i);
-            v[8 * i + 0] += bf16_lo(sv.x); v[8 * i + 1] += bf16_hi(sv.x);
-            v[8 * i + 2] += bf16_lo(sv.y); v[8 * i + 3] += bf16_hi(sv.y);
-            v[8 * i + 4] += bf16_lo(sv.z); v[8 * i + 5] += bf16_hi(sv.z);
-            v[8 * i + 6] += bf16_lo(sv.w); v[8 * i + 7] += bf16_hi(sv.w);
+            const float2 s0 = unpack_h(sv.x, p.f16), s1 = unpack_h(sv.y, p.f16), s2 = unpack_h(sv.z, p.f16), s3 = unpack_h(sv.w, p.f16);
+            v[8 * i + 0] += s0.x; v[8 * i + 1] += s0.y;
+            v[8 * i + 2] += s1.x; v[8 * i + 3] += s1.y;
+            v[8 * i + 4] += s2.x; v[8 * i + 5] += s2.y;
+            v[8 * i + 6] += s3.x; v[8 * i + 7] += s3.y;
           }
         }
         if (p.act == 1) {
@@ -422,10 +425,10 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const uint32_
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             uint4 o;
-            o.x = pack_bf16(v[8 * i + 0], v[8 * i + 1]);
-            o.y = pack_bf16(v[8 * i + 2], v[8 * i + 3]);
-            o.z = pack_bf16(v[8 * i + 4], v[8 * i + 5]);
-            o.w = pack_bf16(v[8 * i + 6], v[8 * i + 7]);
+            o.x = pack_h(v[8 * i + 0], v[8 * i + 1], p.f16);
+            o.y = pack_h(v[8 * i + 2], v[8 * i + 3], p.f16);
+            o.z = pack_h(v[8 * i + 4], v[8 * i + 5], p.f16);
+            o.w = pack_h(v[8 * i + 6], v[8 * i + 7], p.f16);
             *reinterpret_cast<uint4*>(stg + lane * 64 + ((i ^ ((lane >> 1) & 3)) << 4)) = o;   // 64B-swizzled tile
           }
           fence_proxy_async();
@@ -440,10 +443,10 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const uint32_
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           uint4 o;
-          o.x = pack_bf16(v[8 * i + 0], v[8 * i + 1]);
-          o.y = pack_bf16(v[8 * i + 2], v[8 * i + 3]);
-          o.z = pack_bf16(v[8 * i + 4], v[8 * i + 5]);
-          o.w = pack_bf16(v[8 * i + 6], v[8 * i + 7]);
+          o.x = pack_h(v[8 * i + 0], v[8 * i + 1], p.f16);
+          o.y = pack_h(v[8 * i + 2], v[8 * i + 3], p.f16);
+          o.z = pack_h(v[8 * i + 4], v[8 * i + 5], p.f16);
+          o.w = pack_h(v[8 * i + 6], v[8 * i + 7], p.f16);
           d4[i] = o;
         }
       }
@@ -536,7 +539,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(GEMM_BM, BN, 0, 0);
+      const uint32_t idesc = make_idesc_bf16(GEMM_BM, BN, 0, 0) & ~(p.f16 ? IDESC_BF16_BITS : 0u);
       int s = 0;
       uint32_t ph = 0;
       int as = 0;
@@ -686,7 +689,7 @@ headtail_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(GEMM_BM, 32, 0, 0);
+      const uint32_t idesc = make_idesc_bf16(GEMM_BM, 32, 0, 0) & ~(p.f16 ? IDESC_BF16_BITS : 0u);
       int s = 0;
       uint32_t ph = 0;
       int as = 0;
@@ -881,8 +884,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   } else if (warp == 1) {
     // ===================== MMA issuer (pair leader only) =====================
     if (leader && lane == 0) {
-      constexpr uint32_t idesc_full = make_idesc_bf16(256, BN, 0, 0);
-      constexpr uint32_t idesc_half = make_idesc_bf16(256, BN / 2, 0, 0);
+      const uint32_t fmt_clear = ~(p.f16 ? IDESC_BF16_BITS : 0u);
+      const uint32_t idesc_full = make_idesc_bf16(256, BN, 0, 0) & fmt_clear;
+      const uint32_t idesc_half = make_idesc_bf16(256, BN / 2, 0, 0) & fmt_clear;
       int s = 0;
       uint32_t ph = 0;
       int as = 0;

@@ -221,7 +221,7 @@ extern "C" {
 
 void ovg_debug_set_attn_profile(long long* buf) { g_attn_prof = buf; }
 
-int ovg_version(void) { return 2; }
+int ovg_version(void) { return 3; }
 const char* ovg_last_error(void) { return g_err.c_str(); }
 long long ovg_launch_count(void) { return g_launches.load(); }
 
@@ -257,6 +257,7 @@ int ovg_gemm(const ovg_gemm_args* a, void* stream) {
   p.ldo = a->ldo;
   p.table = a->table;
   p.table_rows = a->table_rows > 0 ? a->table_rows : 1;
+  p.f16 = (a->f16 && (a->epi == OVG_EPI_BF16 || a->epi == OVG_EPI_HEADTAIL)) ? 1 : 0;
   p.skip1 = reinterpret_cast<const __nv_bfloat16*>(a->skip1);
   p.skip2 = reinterpret_cast<const __nv_bfloat16*>(a->skip2);
   p.rowmap = a->rowmap;
@@ -455,6 +456,7 @@ int ovg_attention(const void* q, const void* k, const void* v, void* out, int ba
 int ovg_layernorm(const void* in, int in_is_bf16, long long ld_in, void* out, int out_is_f32, long long ld_out, int rows,
                   int C, const float* w, const float* b, float eps, int grp_out, int grp_in, int grp_off, void* stream) {
   OVG_REQUIRE(in && out && rows > 0, "null operand");
+  OVG_REQUIRE(out_is_f32 >= 0 && out_is_f32 <= 2, "output type: 0 bf16, 1 fp32, 2 fp16");
   OVG_REQUIRE((w == nullptr) == (b == nullptr), "affine needs both weight and bias");
   OVG_REQUIRE(C % 128 == 0 && C <= 2048, "C must be a multiple of 128, <= 2048");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -567,14 +569,14 @@ int ovg_im2col3x3s2(const void* src, void* dst, int F, int h, int w, int C, void
 }
 
 int ovg_upsample_bilinear(const void* src, void* dst, const float* tx, const float* ty, int F, int h, int w, int H, int W,
-                          int C, void* stream) {
+                          int C, int f16, void* stream) {
   OVG_REQUIRE(src && dst && F > 0 && h > 0 && w > 0 && H > 0 && W > 0 && C % 16 == 0, "bad arguments");
   OVG_REQUIRE((tx == nullptr) == (ty == nullptr), "position tables come as a pair");
   OVG_REQUIRE(F <= 65535 && H + 2 <= 65535, "grid too large");
   ovg::UpsampleParams p{reinterpret_cast<const __nv_bfloat16*>(src), reinterpret_cast<__nv_bfloat16*>(dst), tx, ty,
                         F, h, w, H, W, C,
                         H > 1 ? static_cast<float>(h - 1) / static_cast<float>(H - 1) : 0.f,
-                        W > 1 ? static_cast<float>(w - 1) / static_cast<float>(W - 1) : 0.f};
+                        W > 1 ? static_cast<float>(w - 1) / static_cast<float>(W - 1) : 0.f, f16 ? 1 : 0};
   const size_t row_smem = static_cast<size_t>(w) * 32 * sizeof(float);
   if (C % 32 == 0 && row_smem <= 48 * 1024 && C / 32 <= 65535) {
     dim3 grid(H + 2, F, C / 32);

@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -250,6 +251,8 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn_ma
          (static_cast<uint32_t>(b_mn_major) << 16) | (static_cast<uint32_t>(N >> 3) << 17) |
          (static_cast<uint32_t>(M >> 4) << 24);
 }
+// Same with IEEE half operands (a_format = b_format = 0): the only difference is bits 7 and 10.
+constexpr uint32_t IDESC_BF16_BITS = (1u << 7) | (1u << 10);
 
 // TMEM -> registers: this thread's lane (32*(warp%4)+lane), 32 / 16 consecutive 32-bit columns.
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
@@ -300,5 +303,17 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 }
 __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
+// IEEE half pair, round to nearest, saturating to +-65504 instead of overflowing to inf (the DPT maps in fp16 mode).
+__device__ __forceinline__ uint32_t pack_f16(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ float2 unpack_f16(uint32_t v) { return __half22float2(*reinterpret_cast<const __half2*>(&v)); }
+// 16-bit storage selected at run time (uniform per launch): f16 != 0 -> IEEE half, else bf16.
+__device__ __forceinline__ uint32_t pack_h(float lo, float hi, int f16) { return f16 ? pack_f16(lo, hi) : pack_bf16(lo, hi); }
+__device__ __forceinline__ float2 unpack_h(uint32_t v, int f16) {
+  return f16 ? unpack_f16(v) : make_float2(bf16_lo(v), bf16_hi(v));
+}
 
 }  // namespace ovg

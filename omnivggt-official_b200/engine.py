@@ -26,9 +26,16 @@ def _f32(t: torch.Tensor) -> torch.Tensor:
     return t.detach().to(F32).contiguous()
 
 
-def _conv3x3_w(w: torch.Tensor) -> torch.Tensor:
+def _half(t: torch.Tensor, dtype) -> torch.Tensor:
+    """16-bit kernel operand: bf16, or fp16 clamped to the finite range."""
+    if dtype == torch.float16:
+        return t.detach().float().clamp(-65504.0, 65504.0).to(dtype).contiguous()
+    return t.detach().to(dtype).contiguous()
+
+
+def _conv3x3_w(w: torch.Tensor, dtype=BF16) -> torch.Tensor:
     """[Cout, Cin, 3, 3] -> [Cout, 9*Cin], K order (tap = ky*3+kx, cin): matches the row-shifted tap GEMM."""
-    return _bf(w.permute(0, 2, 3, 1).reshape(w.shape[0], -1))
+    return _half(w.permute(0, 2, 3, 1).reshape(w.shape[0], -1), dtype)
 
 
 @dataclass
@@ -67,9 +74,14 @@ def _block_array(packs: Sequence[BlockPack]):
 
 class DPTPack:
     """Kernel-layout weights of one DPT head.  The shared LayerNorm affine (heads/dpt_head.py:66,:227) is folded
-    into the 1x1 projections: W (g*xhat + b) + c = (W*g) xhat + (W b + c)."""
+    into the 1x1 projections: W (g*xhat + b) + c = (W*g) xhat + (W b + c).  ``dtype``: torch.float16 (default: the reference keeps
+    its heads in fp32 even under autocast, models/omnivggt.py:45; IEEE half has the 11-bit significand of the TF32 convolutions PyTorch
+    runs them with on a GPU, at the bf16 tensor-core rate) or torch.bfloat16 (wider exponent range, 8-bit significand)."""
 
-    def __init__(self, hp):
+    def __init__(self, hp, dtype=torch.float16):
+        self.dtype = dtype
+        _bf = lambda t: _half(t, dtype)                                          # noqa: E731  (all 16-bit operands of this head)
+        _c3 = lambda w: _conv3x3_w(w, dtype)                                     # noqa: E731
         g, b = hp.norm.weight.detach().float(), hp.norm.bias.detach().float()
         self.proj_w, self.proj_b = [], []
         for pr in hp.projects:
@@ -81,9 +93,9 @@ class DPTPack:
         # ConvTranspose2d weight [Cin, Cout, k, k] -> rows (ky, kx, cout), cols cin
         self.up_w = [_bf(r.weight.detach().permute(2, 3, 1, 0).reshape(-1, r.weight.shape[0])) for r in (r0, r1)]
         self.up_b = [_f32(r0.bias), _f32(r1.bias)]
-        self.down_w, self.down_b = _conv3x3_w(r3.weight.detach()), _f32(r3.bias)
+        self.down_w, self.down_b = _c3(r3.weight.detach()), _f32(r3.bias)
         s = hp.scratch
-        self.rn_w = [_conv3x3_w(getattr(s, f"layer{i + 1}_rn").weight.detach()) for i in range(4)]
+        self.rn_w = [_c3(getattr(s, f"layer{i + 1}_rn").weight.detach()) for i in range(4)]
         self.feat = self.rn_w[0].shape[0]
         self.fus = []
         for name in ("refinenet1", "refinenet2", "refinenet3", "refinenet4"):
@@ -92,11 +104,11 @@ class DPTPack:
             for u in ("resConfUnit1", "resConfUnit2"):
                 if hasattr(f, u):
                     ru = getattr(f, u)
-                    d[u] = (_conv3x3_w(ru.conv1.weight.detach()), _f32(ru.conv1.bias),
-                            _conv3x3_w(ru.conv2.weight.detach()), _f32(ru.conv2.bias))
+                    d[u] = (_c3(ru.conv1.weight.detach()), _f32(ru.conv1.bias),
+                            _c3(ru.conv2.weight.detach()), _f32(ru.conv2.bias))
             self.fus.append(d)
-        self.oc1_w, self.oc1_b = _conv3x3_w(s.output_conv1.weight.detach()), _f32(s.output_conv1.bias)
-        self.oc2_w, self.oc2_b = _conv3x3_w(s.output_conv2["0"].weight.detach()), _f32(s.output_conv2["0"].bias)
+        self.oc1_w, self.oc1_b = _c3(s.output_conv1.weight.detach()), _f32(s.output_conv1.bias)
+        self.oc2_w, self.oc2_b = _c3(s.output_conv2["0"].weight.detach()), _f32(s.output_conv2["0"].bias)
         self.w2, self.b2 = _f32(s.output_conv2["2"].weight.detach().flatten(1)), _f32(s.output_conv2["2"].bias)
         self.outc = self.w2.shape[0]
 
@@ -118,6 +130,7 @@ class DPTPack:
         d.down_w, d.down_b = L.ptr(self.down_w), L.ptr(self.down_b)
         d.oc1_w, d.oc1_b, d.oc2_w, d.oc2_b = L.ptr(self.oc1_w), L.ptr(self.oc1_b), L.ptr(self.oc2_w), L.ptr(self.oc2_b)
         d.w2, d.b2 = L.ptr(self.w2), L.ptr(self.b2)
+        d.f16 = int(self.dtype == torch.float16)
         return d
 
 
@@ -205,7 +218,8 @@ class Engine:
             self.h_dino = C.c_void_p()
             L.check(lib.ovg_dino_create(C.byref(dd), C.byref(self.h_dino)))
             self._handles.append((lib.ovg_dino_destroy, self.h_dino))
-        self.dpt_packs = {name: DPTPack(getattr(model, name)) for name in ("depth_head", "point_head")
+        dpt_dtype = {"fp16": torch.float16, "bf16": BF16}[getattr(model, "dpt_dtype", "fp16")]
+        self.dpt_packs = {name: DPTPack(getattr(model, name), dpt_dtype) for name in ("depth_head", "point_head")
                           if getattr(model, name, None) is not None}
         self.h_dpt = {}
         for name, pk in self.dpt_packs.items():

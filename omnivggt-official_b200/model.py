@@ -38,7 +38,7 @@ class OmniVGGT(nn.Module, PyTorchModelHubMixin):
                  dpt_out_channels: Sequence[int] = (256, 512, 1024, 1024),
                  dpt_layers: Sequence[int] = (4, 11, 17, 23), camera_heads: int = 16, camera_trunk_depth: int = 4,
                  dino_backend: str = "ovg", dino_dtype: torch.dtype = torch.bfloat16, camera_backend: str = "ovg",
-                 camera_dtype: torch.dtype = torch.bfloat16,
+                 camera_dtype: torch.dtype = torch.bfloat16, dpt_dtype: str = "fp16",
                  use_cuda_graph: Optional[bool] = None, init_seed: Optional[int] = 0):
         super().__init__()
         self.img_size, self.patch_size, self.embed_dim = img_size, patch_size, embed_dim
@@ -47,6 +47,10 @@ class OmniVGGT(nn.Module, PyTorchModelHubMixin):
         self.dino_dtype = dino_dtype
         self.camera_backend = camera_backend  # "ovg": camera head on the libovg runtime; "torch": library kernels
         self.camera_dtype = camera_dtype     # camera_backend="torch": precision of the weight matrices (fp32 selectable)
+        # DPT heads: "fp16" (11-bit significand like the TF32 convolutions the reference's fp32 heads run with on a GPU; stores
+        # saturate at +-65504) or "bf16" (8-bit significand, fp32 exponent range).  Same speed; see DESIGN.md section 2.
+        assert dpt_dtype in ("fp16", "bf16")
+        self.dpt_dtype = dpt_dtype
         # replay the ~1000 kernel launches of a forward from a CUDA graph once a shape has been seen twice
         self.use_cuda_graph = (os.environ.get("OVG_CUDA_GRAPH", "1") != "0") if use_cuda_graph is None else use_cuda_graph
         self._graphs = {}

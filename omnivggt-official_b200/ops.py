@@ -24,9 +24,17 @@ def _chk(t: torch.Tensor, dtype, name: str):
 
 def gemm(a: torch.Tensor, b: torch.Tensor, *, m: Optional[int] = None, taps: Optional[Sequence[int]] = None,
          epi: int = L.EPI_BF16, block_n: int = 0, **kw) -> None:
-    """a: bf16 [rows, a_cols] (last dim contiguous), b: bf16 [n, taps*a_cols].  kw: fields of ovg_gemm_args."""
-    _chk(a, BF16, "a")
-    _chk(b, BF16, "b")
+    """a: bf16 [rows, a_cols] (last dim contiguous), b: bf16 [n, taps*a_cols] -- or both fp16 (EPI_BF16 / EPI_HEADTAIL only:
+    skips and the output are then fp16 too).  kw: fields of ovg_gemm_args."""
+    F16 = torch.float16
+    if a.dtype == F16:
+        assert epi in (L.EPI_BF16, L.EPI_HEADTAIL), "fp16 operands: EPI_BF16 / EPI_HEADTAIL only"
+        _chk(a, F16, "a")
+        _chk(b, F16, "b")
+        kw = dict(kw, f16=1)
+    else:
+        _chk(a, BF16, "a")
+        _chk(b, BF16, "b")
     assert a.dim() == 2 and b.dim() == 2 and a.stride(1) == 1 and b.stride(1) == 1
     taps = list(taps) if taps is not None else [0]
     assert b.shape[1] == a.shape[1] * len(taps), (tuple(a.shape), tuple(b.shape), len(taps))
@@ -99,12 +107,12 @@ def attention_kv(q, k, v, out, batch: int, heads: int, nq: int, nkv: int):
 
 
 def layernorm(x, out, w=None, b=None, eps=1e-5, rows=None, grp_out=0, grp_in=0, grp_off=0):
-    assert x.dtype in (F32, BF16) and out.dtype in (F32, BF16) and x.stride(-1) == 1 and out.stride(-1) == 1
+    assert x.dtype in (F32, BF16) and out.dtype in (F32, BF16, torch.float16) and x.stride(-1) == 1 and out.stride(-1) == 1
     x2 = x if x.dim() == 2 else x.reshape(-1, x.shape[-1])
     o2 = out if out.dim() == 2 else out.reshape(-1, out.shape[-1])
     rows = o2.shape[0] if rows is None else rows
-    L.check(L.lib().ovg_layernorm(x2.data_ptr(), int(x.dtype == BF16), x2.stride(0), o2.data_ptr(), int(out.dtype == F32),
-                                  o2.stride(0), rows,
+    L.check(L.lib().ovg_layernorm(x2.data_ptr(), int(x.dtype == BF16), x2.stride(0), o2.data_ptr(),
+                                  {BF16: 0, F32: 1, torch.float16: 2}[out.dtype], o2.stride(0), rows,
                                   o2.shape[1], L.ptr(w), L.ptr(b), eps, grp_out, grp_in, grp_off, L.stream()))
     return out
 
@@ -139,8 +147,10 @@ def im2col3x3s2(src, dst, F, h, w, C):
 
 
 def upsample_bilinear(src, dst, tx, ty, F, h, w, H, W, C):
-    """tx [W, C/2], ty [H, C/2]: separable UV position embedding (or both None)."""
-    L.check(L.lib().ovg_upsample_bilinear(src.data_ptr(), dst.data_ptr(), L.ptr(tx), L.ptr(ty), F, h, w, H, W, C, L.stream()))
+    """tx [W, C/2], ty [H, C/2]: separable UV position embedding (or both None); src / dst both bf16 or both fp16."""
+    assert src.dtype == dst.dtype and src.dtype in (BF16, torch.float16)
+    L.check(L.lib().ovg_upsample_bilinear(src.data_ptr(), dst.data_ptr(), L.ptr(tx), L.ptr(ty), F, h, w, H, W, C,
+                                          int(src.dtype == torch.float16), L.stream()))
 
 
 def pose_decode(pose_enc, H: int, W: int):

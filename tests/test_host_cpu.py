@@ -39,7 +39,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/ovg.h but not exported by libovg.so"
     assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
-    assert lib.ovg_version() == 2
+    assert lib.ovg_version() == 3
 
 
 def test_ctypes_struct_matches_header():

@@ -420,6 +420,104 @@ def test_head_tail(outc, act):
     assert rel(preds, pr) < 1e-2 and rel(conf, 1 + y[..., -1].exp()) < 1e-2
 
 
+# ----------------------------------------------------------------------------------------------- fp16 mode of the DPT kernels
+# The DPT heads run with IEEE-half operands / maps by default (ovg_gemm_args.f16, ovg_dpt_desc.f16): same kernels, the instruction
+# descriptor's operand format and the 16-bit pack / unpack differ.  fp16 rounds to 2^-12 relative: tolerances are 8 x tighter.
+F16 = torch.float16
+
+
+@pytest.mark.parametrize("M,N,K,bn", [(300, 256, 128, 0), (1000, 384, 192, 128), (77, 96, 392, 64), (2748, 1024, 1024, 512),
+                                      (5000, 1024, 128, 512), (2748, 384, 192, 384)])
+def test_fp16_gemm_bias_gelu(M, N, K, bn):
+    ops = _ops()
+    a = randn(M, K, seed=1, dtype=F16)
+    w = randn(N, K, scale=K ** -0.5, seed=2, dtype=F16)
+    bias = randn(N, seed=3)
+    out = torch.empty(M, N, device="cuda", dtype=F16)
+    ops.gemm(a, w, epi=ops.L.EPI_BF16, bias=bias, act=ops.L.ACT_GELU, out=out, ldo=N, block_n=bn)
+    ref = F.gelu(a.float() @ w.float().t() + bias)
+    torch.cuda.synchronize()
+    assert rel(out, ref) < 8e-4
+
+
+@pytest.mark.parametrize("Fr,h,w,Cin,Cout,bn", [(2, 9, 7, 64, 64, 0), (1, 37, 37, 256, 256, 512), (2, 30, 30, 256, 128, 384)])
+def test_fp16_conv3x3_taps_with_skips_relu(Fr, h, w, Cin, Cout, bn):
+    ops = _ops()
+    x = randn(Fr, Cin, h, w, seed=1)
+    wt = randn(Cout, Cin, 3, 3, scale=(9 * Cin) ** -0.5, seed=2)
+    bias = randn(Cout, seed=3)
+    s1, s2 = randn(Fr, Cout, h, w, seed=4), randn(Fr, Cout, h, w, seed=5)
+    xp, s1p, s2p = _to_pad(x).to(F16), _to_pad(s1).to(F16), _to_pad(s2).to(F16)
+    wb = wt.permute(0, 2, 3, 1).reshape(Cout, 9 * Cin).to(F16).contiguous()
+    outp = torch.full((Fr, h + 2, w + 2, Cout), 7.0, device="cuda", dtype=F16)
+    taps = [(ky - 1) * (w + 2) + (kx - 1) for ky in range(3) for kx in range(3)]
+    ops.gemm(xp.reshape(-1, Cin), wb, taps=taps, epi=ops.L.EPI_BF16, bias=bias, act=ops.L.ACT_RELU, out=outp,
+             ldo=Cout, skip1=s1p, skip2=s2p, rowmap=ops.L.ROWS_PAD, gh=h, gw=w, block_n=bn)
+    ref = F.relu(F.conv2d(_from_pad(xp), wb.float().reshape(Cout, 3, 3, Cin).permute(0, 3, 1, 2), bias, padding=1)
+                 + _from_pad(s1p) + _from_pad(s2p))
+    torch.cuda.synchronize()
+    assert rel(_from_pad(outp), ref) < 8e-4
+    border = outp.clone()
+    border[:, 1:-1, 1:-1] = 0
+    assert (border == 0).all()
+
+
+def test_fp16_stores_saturate_instead_of_overflowing():
+    """|acc| > 65504 is stored as +-65504, never inf (cvt.rn.satfinite.f16x2.f32)."""
+    ops = _ops()
+    a = torch.full((256, 64), 64.0, device="cuda", dtype=F16)
+    w = torch.full((64, 64), 32.0, device="cuda", dtype=F16)
+    w[1::2] = -32.0
+    out = torch.empty(256, 64, device="cuda", dtype=F16)
+    ops.gemm(a, w, epi=ops.L.EPI_BF16, out=out, ldo=64)          # acc = +-131072
+    torch.cuda.synchronize()
+    assert torch.isfinite(out).all()
+    assert (out[:, 0::2] == 65504).all() and (out[:, 1::2] == -65504).all()
+
+
+@pytest.mark.parametrize("h,w,H,W,C", [(4, 4, 8, 8, 64), (19, 19, 37, 37, 256), (8, 12, 14, 21, 144)])
+def test_fp16_upsample_bilinear(h, w, H, W, C):
+    ops = _ops()
+    Fr = 2
+    x = randn(Fr, C, h, w, seed=1)
+    tx, ty = randn(W, C // 2, seed=2), randn(H, C // 2, seed=3)
+    xp = _to_pad(x).to(F16)
+    dst = torch.full((Fr, H + 2, W + 2, C), 3.0, device="cuda", dtype=F16)
+    ops.upsample_bilinear(xp, dst, tx, ty, Fr, h, w, H, W, C)
+    ref = F.interpolate(_from_pad(xp), size=(H, W), mode="bilinear", align_corners=True)
+    table = torch.cat([tx[None, :, :].expand(H, W, C // 2), ty[:, None, :].expand(H, W, C // 2)], -1)
+    assert rel(_from_pad(dst), ref + table.permute(2, 0, 1)) < 6e-4
+    b = dst.clone()
+    b[:, 1:-1, 1:-1] = 0
+    assert (b == 0).all()
+
+
+def test_fp16_layernorm_out_and_head_tail():
+    ops = _ops()
+    C, T, P = 2048, 21, 16
+    xb = randn(4 * T, C, seed=4, dtype=BF16)
+    out = torch.empty(4 * P, C, device="cuda", dtype=F16)
+    ops.layernorm(xb, out, None, None, 1e-5, grp_out=P, grp_in=T, grp_off=5)
+    ref = F.layer_norm(xb.float().reshape(4, T, C)[:, 5:], (C,), None, None, 1e-5).reshape(4 * P, C)
+    assert rel(out, ref) < 5e-4
+    Fr, h, w, Cin, outc = 2, 14, 28, 128, 4
+    x = randn(Fr, Cin, h, w, seed=1)
+    w1 = randn(32, Cin, 3, 3, scale=(9 * Cin) ** -0.5, seed=2)
+    b1, w2, b2 = randn(32, scale=0.1, seed=3), randn(outc, 32, scale=32 ** -0.5, seed=4), randn(outc, scale=0.1, seed=5)
+    xp = _to_pad(x).to(F16)
+    wb = w1.permute(0, 2, 3, 1).reshape(32, 9 * Cin).to(F16).contiguous()
+    preds = torch.zeros(Fr, h, w, outc - 1, device="cuda")
+    conf = torch.zeros(Fr, h, w, device="cuda")
+    taps = [(ky - 1) * (w + 2) + (kx - 1) for ky in range(3) for kx in range(3)]
+    ops.gemm(xp.reshape(-1, Cin), wb, taps=taps, epi=ops.L.EPI_HEADTAIL, bias=b1, w2=w2.contiguous(), b2=b2, outc=outc,
+             head_act=1, preds=preds, conf=conf, rowmap=ops.L.ROWS_PAD, gh=h, gw=w)
+    y = F.conv2d(_from_pad(xp), wb.float().reshape(32, 3, 3, Cin).permute(0, 3, 1, 2), b1, padding=1)
+    y = F.conv2d(F.relu(y), w2[:, :, None, None], b2).permute(0, 2, 3, 1)
+    pr = torch.sign(y[..., :-1]) * torch.expm1(y[..., :-1].abs())
+    torch.cuda.synchronize()
+    assert rel(preds, pr) < 1e-4 and rel(conf, 1 + y[..., -1].exp()) < 1e-4
+
+
 # ----------------------------------------------------------------------------------------------- C host
 def test_c_host_drives_the_runtime(tmp_path):
     """A plain C program (tests/c/runtime_identity.c: gcc, libovg + libcudart, no Python / torch in the process) runs the
