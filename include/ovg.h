@@ -141,6 +141,20 @@ int ovg_im2col3x3s2(const void* src, void* dst, int F, int h, int w, int C, void
 int ovg_upsample_bilinear(const void* src, void* dst, const float* tx, const float* ty, int F, int h, int w, int H, int W,
                           int C, int f16, void* stream);
 
+/* Fused DPT output tail (heads/dpt_head.py:242-260, heads/head_act.py:61-125): bilinear resize (align_corners=True) of the
+ * zero-bordered 16-bit NHWC map src [F, h+2, w+2, 128] to H x W, + UV position embedding (tx fp32 [W, 64], ty fp32 [H, 64], or both
+ * NULL), 3x3 conv 128 -> 32 (w3x3: 16-bit [32, 9*128], K order (ky, kx, c); bias fp32 [32]), ReLU, 1x1 conv 32 -> outc (w2 fp32
+ * [outc, 32], b2), activations (head_act 0: exp, 1: inverse-log; confidence 1 + exp) -> preds fp32 [F, H, W, outc-1], conf fp32
+ * [F, H, W].  The H x W x 128 map is never materialised: the resized rows go straight into the tensor-core operand (rounded to 16
+ * bits), and the position embedding enters through its own image under the 3x3 kernel, added in fp32 (the convolution is linear).
+ * f16: src / w3x3 are fp16 (else bf16).  scratch: ovg_dpt_tail_scratch_bytes(H, W) bytes, 16-byte aligned (unused when tx is NULL).
+ * ovg_dpt_tail_supported: 1 if the geometry fits the kernel (C == 128, upsampling, <= 80 source pixels under a 130-pixel strip). */
+int ovg_dpt_tail_supported(int h, int w, int H, int W, int C);
+long long ovg_dpt_tail_scratch_bytes(int H, int W);
+int ovg_dpt_tail(const void* src, const float* tx, const float* ty, const void* w3x3, const float* bias, const float* w2,
+                 const float* b2, int outc, int head_act, float* preds, float* conf, int F, int h, int w, int H, int W, int f16,
+                 void* scratch, void* stream);
+
 /* GPU input pipeline: the per-view work of visual_util.py:719-841 (load_images_and_cameras) on
  * decoded pixels.  The tap / index tables are small per-image-size arrays computed by the host with the libraries' own arithmetic
  * (Pillow Resample.c precompute_coeffs + normalize_coeffs_8bpc; OpenCV resizeNN).

@@ -9,8 +9,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc", "ovg.cu")
 OUT = os.path.join(HERE, "libovg.so")
-DEPS = [os.path.join(HERE, "csrc", f) for f in ("ovg.cu", "gemm.cuh", "attn.cuh", "elem.cuh", "ptx.cuh")] + [
-    os.path.join(os.path.dirname(HERE), "include", "ovg.h")]
+DEPS = sorted(os.path.join(HERE, "csrc", f) for f in os.listdir(os.path.join(HERE, "csrc"))
+              if f.endswith((".cu", ".cuh", ".inc", ".h"))) + [os.path.join(os.path.dirname(HERE), "include", "ovg.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-shared",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 

@@ -14,6 +14,7 @@
 #include "elem.cuh"
 #include "gemm.cuh"
 #include "post.cuh"
+#include "tail.cuh"
 #include "pre.cuh"
 
 namespace {
@@ -216,10 +217,12 @@ int dispatch_bn(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const ovg:
 }  // namespace
 
 long long* g_attn_prof = nullptr;   // set through ovg_debug_set_attn_profile (profiling builds)
+long long* g_tail_prof = nullptr;   // ovg_debug_set_tail_profile: clock64 stamps of the fused DPT tail (csrc/tail.cuh)
 
 extern "C" {
 
 void ovg_debug_set_attn_profile(long long* buf) { g_attn_prof = buf; }
+void ovg_debug_set_tail_profile(long long* buf) { g_tail_prof = buf; }
 
 int ovg_version(void) { return 3; }
 const char* ovg_last_error(void) { return g_err.c_str(); }
@@ -587,6 +590,68 @@ int ovg_upsample_bilinear(const void* src, void* dst, const float* tx, const flo
   dim3 grid((per_row + 255) / 256, H + 2, F);
   ovg::upsample_bilinear_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
   return post_launch("ovg_upsample_bilinear");
+}
+
+int ovg_dpt_tail_supported(int h, int w, int H, int W, int C) {
+  if (C != 128 || h < 2 || w < 2 || H < h || W < w) return 0;
+  const float sx = W > 1 ? static_cast<float>(w - 1) / static_cast<float>(W - 1) : 0.f;
+  const int span = static_cast<int>(sx * 129.0f) + 3;           // source pixels under 130 output pixels
+  return span <= ovg::FT_VBUF_PX ? 1 : 0;
+}
+
+long long ovg_dpt_tail_scratch_bytes(int H, int W) { return (H > 0 && W > 0) ? 3LL * (H + W) * 32 * 4 : -1; }
+
+int ovg_dpt_tail(const void* src, const float* tx, const float* ty, const void* w3x3, const float* bias, const float* w2,
+                 const float* b2, int outc, int head_act, float* preds, float* conf, int F, int h, int w, int H, int W, int f16,
+                 void* scratch, void* stream) {
+  OVG_REQUIRE(src && w3x3 && bias && w2 && b2 && preds && conf, "null argument");
+  OVG_REQUIRE((tx == nullptr) == (ty == nullptr), "position tables come as a pair");
+  OVG_REQUIRE(tx == nullptr || (scratch && (reinterpret_cast<uintptr_t>(scratch) & 15) == 0),
+              "position embedding needs 16-byte aligned scratch (ovg_dpt_tail_scratch_bytes)");
+  OVG_REQUIRE(H >= 2 && W >= 2, "image too small");
+  OVG_REQUIRE(F > 0 && outc >= 2 && outc <= 4, "bad arguments");
+  OVG_REQUIRE(ovg_dpt_tail_supported(h, w, H, W, 128), "unsupported geometry (ovg_dpt_tail_supported)");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  CUtensorMap tb;
+  int rc = get_map(w3x3, 9 * 128, 32, 0, 9 * 128, 32, &tb);
+  if (rc) return rc;
+  ovg::TailParams p{};
+  p.src = reinterpret_cast<const uint16_t*>(src);
+  if (tx) {
+    float* gx = static_cast<float*>(scratch);
+    float* gy = gx + 3LL * W * 32;
+    ovg::TailTableParams tp{tx, ty, reinterpret_cast<const uint16_t*>(w3x3), gx, gy, H, W, f16 ? 1 : 0};
+    ovg::tail_tables_kernel<<<dim3(W > H ? W : H, 2), 96, 0, st>>>(tp);
+    rc = post_launch("ovg_dpt_tail(tables)");
+    if (rc) return rc;
+    p.gx = gx; p.gy = gy;
+  }
+  p.bias = bias; p.w2 = w2; p.b2 = b2; p.preds = preds; p.conf = conf;
+  p.F = F; p.h = h; p.w = w; p.H = H; p.W = W;
+  p.sy = H > 1 ? static_cast<float>(h - 1) / static_cast<float>(H - 1) : 0.f;
+  p.sx = W > 1 ? static_cast<float>(w - 1) / static_cast<float>(W - 1) : 0.f;
+  p.outc = outc; p.head_act = head_act; p.f16 = f16 ? 1 : 0;
+  p.n_strips = (W + 127) / 128;
+  // segments of rows per (frame, strip): about three work items per SM, each paying two halo rows
+  const int sms = num_sms();
+  int segs = (3 * sms + F * p.n_strips - 1) / (F * p.n_strips);
+  if (segs < 1) segs = 1;
+  if (segs > H) segs = H;
+  p.seg_rows = (H + segs - 1) / segs;
+  if (p.seg_rows < 8 && H >= 8) p.seg_rows = 8;
+  p.n_segs = (H + p.seg_rows - 1) / p.seg_rows;
+  p.n_items = F * p.n_strips * p.n_segs;
+  p.prof = g_tail_prof;
+  static PerDeviceOnce once;
+  if (once.needed()) {
+    OVG_CUDA(cudaFuncSetAttribute(ovg::fusedtail_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ovg::FT_SMEM_BYTES));
+    OVG_CUDA(cudaFuncSetAttribute(ovg::fusedtail_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ovg::FT_SMEM_BYTES));
+    once.mark_done();
+  }
+  const int grid = p.n_items < sms ? p.n_items : sms;
+  if (p.f16) ovg::fusedtail_kernel<true><<<grid, ovg::FT_THREADS, ovg::FT_SMEM_BYTES, st>>>(tb, p);
+  else ovg::fusedtail_kernel<false><<<grid, ovg::FT_THREADS, ovg::FT_SMEM_BYTES, st>>>(tb, p);
+  return post_launch("ovg_dpt_tail");
 }
 
 int ovg_preprocess_image(const unsigned char* src, int h, int w, int nw, int nh, int crop, int fh, const int* hmin, const int* hcnt,

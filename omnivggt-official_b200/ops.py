@@ -153,6 +153,20 @@ def upsample_bilinear(src, dst, tx, ty, F, h, w, H, W, C):
                                           int(src.dtype == torch.float16), L.stream()))
 
 
+def dpt_tail(src, tx, ty, w3x3, bias, w2, b2, head_act: int, F: int, h: int, w: int, H: int, W: int):
+    """Fused resize + position embedding + 3x3 conv 128->32 + ReLU + 1x1 + activations (ovg_dpt_tail).  src: zero-bordered
+    [F, h+2, w+2, 128] bf16 / fp16; w3x3 [32, 9*128] same dtype.  Returns (preds fp32 [F,H,W,outc-1], conf fp32 [F,H,W])."""
+    assert src.dtype == w3x3.dtype and src.dtype in (BF16, torch.float16) and src.is_contiguous() and w3x3.is_contiguous()
+    outc = w2.shape[0]
+    preds = torch.empty(F, H, W, outc - 1, device=src.device, dtype=F32)
+    conf = torch.empty(F, H, W, device=src.device, dtype=F32)
+    scratch = torch.empty(L.lib().ovg_dpt_tail_scratch_bytes(H, W), device=src.device, dtype=torch.uint8)
+    L.check(L.lib().ovg_dpt_tail(src.data_ptr(), L.ptr(tx), L.ptr(ty), w3x3.data_ptr(), bias.data_ptr(), w2.data_ptr(), b2.data_ptr(),
+                                 outc, head_act, preds.data_ptr(), conf.data_ptr(), F, h, w, H, W, int(src.dtype == torch.float16),
+                                 scratch.data_ptr(), L.stream()))
+    return preds, conf
+
+
 def pose_decode(pose_enc, H: int, W: int):
     """pose_enc fp32 [..., 9] -> (extrinsic [..., 3, 4], intrinsic [..., 3, 3], cam2world [..., 3, 4]) on the device."""
     _chk(pose_enc, F32, "pose_enc")

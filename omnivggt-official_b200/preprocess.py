@@ -107,7 +107,7 @@ def preprocess_views(images: Sequence, cameras: Optional[Sequence] = None, depth
     st = L.stream()
     keep = []
     for i, (im, (h, w, _, nh, crop, _)) in enumerate(zip(images, geoms)):
-        src = torch.as_tensor(np.ascontiguousarray(im) if isinstance(im, np.ndarray) else im, dtype=torch.uint8).to(dev).contiguous()
+        src = torch.as_tensor(np.array(im, dtype=np.uint8, copy=True) if isinstance(im, np.ndarray) else im, dtype=torch.uint8).to(dev).contiguous()
         assert src.shape == (h, w, 3), "images are uint8 RGB [h, w, 3]"
         hk = bicubic_taps(w, nw, dev) if w != nw else (None, None, None, 0)
         vk = bicubic_taps(h, nh, dev) if h != nh else (None, None, None, 0)

@@ -518,6 +518,45 @@ def test_fp16_layernorm_out_and_head_tail():
     assert rel(preds, pr) < 1e-4 and rel(conf, 1 + y[..., -1].exp()) < 1e-4
 
 
+@pytest.mark.parametrize("dtype", [F16, BF16])
+@pytest.mark.parametrize("Fr,h,w,H,W,outc,act", [(2, 12, 20, 21, 35, 2, 0), (2, 80, 90, 140, 300, 4, 1), (3, 9, 75, 16, 131, 4, 1),
+                                               (1, 296, 296, 518, 518, 2, 0), (2, 37, 37, 37, 64, 4, 1)])
+def test_dpt_tail_fused(Fr, h, w, H, W, outc, act, dtype):
+    """ovg_dpt_tail: resize + position embedding + 3x3 conv 128->32 + ReLU + 1x1 + activations in one kernel (the H x W x 128 map
+    is never written) against PyTorch fp32 (heads/dpt_head.py:242-260), and against the two-kernel path it replaces."""
+    ops = _ops()
+    Cin = 128
+    assert ops.L.lib().ovg_dpt_tail_supported(h, w, H, W, Cin) == 1
+    x = randn(Fr, Cin, h, w, seed=1)
+    w1 = randn(32, Cin, 3, 3, scale=(9 * Cin) ** -0.5, seed=2)
+    b1, w2, b2 = randn(32, scale=0.1, seed=3), randn(outc, 32, scale=32 ** -0.5, seed=4), randn(outc, scale=0.1, seed=5)
+    tx, ty = randn(W, Cin // 2, scale=0.1, seed=6), randn(H, Cin // 2, scale=0.1, seed=7)
+    xp = _to_pad(x).to(dtype)
+    wb = w1.permute(0, 2, 3, 1).reshape(32, 9 * Cin).to(dtype).contiguous()
+    preds, conf = ops.dpt_tail(xp, tx, ty, wb, b1, w2.contiguous(), b2, act, Fr, h, w, H, W)
+    torch.cuda.synchronize()
+    up = F.interpolate(_from_pad(xp), size=(H, W), mode="bilinear", align_corners=True)
+    up = up.to(dtype).float()                          # the kernel rounds the resized operand to 16 bits; the embedding stays fp32
+    up = up + torch.cat([tx[None, :, :].expand(H, W, Cin // 2), ty[:, None, :].expand(H, W, Cin // 2)], -1).permute(2, 0, 1)
+    y = F.conv2d(up, wb.float().reshape(32, 3, 3, Cin).permute(0, 3, 1, 2), b1, padding=1)
+    y = F.conv2d(F.relu(y), w2[:, :, None, None], b2).permute(0, 2, 3, 1)
+    pr = torch.exp(y[..., :-1]) if act == 0 else torch.sign(y[..., :-1]) * torch.expm1(y[..., :-1].abs())
+    tol = 2e-3 if dtype == F16 else 1.2e-2              # re-rounding of `up` may differ by one ulp of the 16-bit type from torch's
+    assert torch.isfinite(preds).all() and torch.isfinite(conf).all()
+    assert rel(preds, pr) < tol and rel(conf, 1 + y[..., -1].exp()) < tol, (rel(preds, pr), rel(conf, 1 + y[..., -1].exp()))
+    # the path it replaces: ovg_upsample_bilinear -> HEADTAIL GEMM
+    dst = torch.zeros(Fr, H + 2, W + 2, Cin, device="cuda", dtype=dtype)
+    ops.upsample_bilinear(xp, dst, tx, ty, Fr, h, w, H, W, Cin)
+    p2 = torch.zeros(Fr, H, W, outc - 1, device="cuda")
+    c2 = torch.zeros(Fr, H, W, device="cuda")
+    taps = [(ky - 1) * (W + 2) + (kx - 1) for ky in range(3) for kx in range(3)]
+    ops.gemm(dst.reshape(-1, Cin), wb, taps=taps, epi=ops.L.EPI_HEADTAIL, bias=b1, w2=w2.contiguous(), b2=b2, outc=outc,
+             head_act=act, preds=p2, conf=c2, rowmap=ops.L.ROWS_PAD, gh=H, gw=W)
+    torch.cuda.synchronize()
+    tol2 = 1e-3 if dtype == F16 else 8e-3              # that path rounds (map + embedding) to 16 bits, this one the map only
+    assert rel(preds, p2) < tol2 and rel(conf, c2) < tol2, (rel(preds, p2), rel(conf, c2))
+
+
 # ----------------------------------------------------------------------------------------------- C host
 def test_c_host_drives_the_runtime(tmp_path):
     """A plain C program (tests/c/runtime_identity.c: gcc, libovg + libcudart, no Python / torch in the process) runs the
