@@ -20,6 +20,8 @@ struct AttnParams {
   int C;        // heads * 64 (row stride of `out`)
   __nv_bfloat16* out;  // [batch, n, C]
   long long* prof;     // optional [2][8] cycle counters (OVG_ATT_PROFILE builds only)
+  int q_tiles;         // ceil(n / 128)
+  int items;           // batch * heads * q_tiles work items, walked by the persistent grid (item = bh * q_tiles + q tile)
 };
 #ifdef OVG_ATT_PROFILE
 #define ATT_T(var) const long long var = clock64()
@@ -96,13 +98,12 @@ attn1_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
   uint64_t* p_full = s_full + 1;       // [1]
   uint64_t* o_ready = p_full + 1;      // [1]
   uint64_t* s_taken = o_ready + 1;     // [1]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_taken + 1);
+  uint64_t* q_empty = s_taken + 1;     // [1] the last S MMA of a work item has been issued: Q may be overwritten
+  uint64_t* o_taken = q_empty + 1;     // [1] the softmax warps hold the finished O tile in registers: O may be overwritten
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_taken + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * 128;
-  const int head = blockIdx.y;
-  const int bh = blockIdx.z * p.heads + head;
   const int nkv = (p.nkv + 127) / 128;
 
   if (warp == 0 && lane == 0) {
@@ -118,6 +119,8 @@ attn1_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
     mbar_init(p_full, 4);
     mbar_init(o_ready, 1);
     mbar_init(s_taken, 4);
+    mbar_init(q_empty, 1);
+    mbar_init(o_taken, 4);
     for (int i = 0; i < NS; ++i) {
       mbar_init(&k_full[i], 1);
       mbar_init(&k_empty[i], 1);
@@ -139,20 +142,24 @@ attn1_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
   if (warp < 4) reg_dealloc<40>();
   if (warp == 0) {
     if (lane == 0) {
-      mbar_expect_tx(q_full, ATT_TILE_BYTES);
-      tma_load_3d(sQ, &tmQ, q_full, 0, q0, bh);
       int s = 0;
-      uint32_t ph = 0;
-      for (int j = 0; j < nkv; ++j) {
-        mbar_wait_quiet(&k_empty[s], ph ^ 1);
-        mbar_expect_tx(&k_full[s], ATT_TILE_BYTES);
-        tma_load_3d(sK + s * ATT_TILE_BYTES, &tmK, &k_full[s], 0, j * 128, bh);
-        mbar_wait_quiet(&v_empty[s], ph ^ 1);
-        mbar_expect_tx(&v_full[s], ATT_TILE_BYTES);
-        tma_load_3d(sV + s * ATT_TILE_BYTES, &tmV, &v_full[s], 0, j * 128, bh);
-        if (++s == NS) {
-          s = 0;
-          ph ^= 1;
+      uint32_t ph = 0, iph = 0;
+      for (int item = blockIdx.x; item < p.items; item += gridDim.x, iph ^= 1) {
+        const int bh = item / p.q_tiles, q0 = (item - bh * p.q_tiles) * 128;
+        mbar_wait_quiet(q_empty, iph ^ 1);          // (first item: passes) the previous item's last S MMA has been issued
+        mbar_expect_tx(q_full, ATT_TILE_BYTES);
+        tma_load_3d(sQ, &tmQ, q_full, 0, q0, bh);
+        for (int j = 0; j < nkv; ++j) {
+          mbar_wait_quiet(&k_empty[s], ph ^ 1);
+          mbar_expect_tx(&k_full[s], ATT_TILE_BYTES);
+          tma_load_3d(sK + s * ATT_TILE_BYTES, &tmK, &k_full[s], 0, j * 128, bh);
+          mbar_wait_quiet(&v_empty[s], ph ^ 1);
+          mbar_expect_tx(&v_full[s], ATT_TILE_BYTES);
+          tma_load_3d(sV + s * ATT_TILE_BYTES, &tmV, &v_full[s], 0, j * 128, bh);
+          if (++s == NS) {
+            s = 0;
+            ph ^= 1;
+          }
         }
       }
     }
@@ -180,31 +187,47 @@ attn1_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
           umma_ts(tO, tP + 8 * k, bdesc + static_cast<uint64_t>(k) * (2048 >> 4), idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
         umma_commit(o_ready);
       };
-      mbar_wait_quiet(q_full, 0);
-      mbar_wait_quiet(&k_full[0], 0);
-      tc_fence_after();
-      issue_S(0);
-      umma_commit(&k_empty[0]);
+      // One flat sequence of KV iterations over all work items of this CTA (`it` counts them: the per-iteration barriers
+      // complete once per iteration).  S of the NEXT iteration -- also across an item boundary, then with the next item's Q --
+      // is issued as soon as the softmax warps hold the current S in registers.
+      int n_items = 0;
+      for (int item = blockIdx.x; item < p.items; item += gridDim.x) ++n_items;
+      if (n_items > 0) {
+        mbar_wait_quiet(q_full, 0);
+        mbar_wait_quiet(&k_full[0], 0);
+        tc_fence_after();
+        issue_S(0);
+        umma_commit(&k_empty[0]);
+        if (nkv == 1) umma_commit(q_empty);
+      }
       int s = 0, sn = 1 % NS;
       uint32_t ph = 0, phn = (NS == 1) ? 1u : 0u;
-      for (int j = 0; j < nkv; ++j) {
-        if (j + 1 < nkv) {              // S(j+1) as soon as the softmax warps hold S(j) in registers
-          mbar_wait_quiet(&k_full[sn], phn);
-          mbar_wait_quiet(s_taken, j & 1);
+      uint32_t it = 0;
+      for (int ii = 0; ii < n_items; ++ii) {
+        for (int j = 0; j < nkv; ++j, ++it) {
+          const bool next_in_item = j + 1 < nkv;
+          if (next_in_item || ii + 1 < n_items) {   // S(next) as soon as the softmax warps hold S(it) in registers
+            if (!next_in_item) mbar_wait_quiet(q_full, (ii + 1) & 1);      // Q of the next work item
+            mbar_wait_quiet(&k_full[sn], phn);
+            mbar_wait_quiet(s_taken, it & 1);
+            tc_fence_after();
+            issue_S(sn);
+            umma_commit(&k_empty[sn]);
+            // that was the last S of its item: Q may be replaced
+            if (next_in_item ? (j + 2 == nkv) : (nkv == 1)) umma_commit(q_empty);
+          }
+          mbar_wait_quiet(&v_full[s], ph);
+          mbar_wait_quiet(p_full, it & 1);
+          if (j == 0 && ii > 0) mbar_wait_quiet(o_taken, (ii - 1) & 1);   // the previous item's O has been read out
           tc_fence_after();
-          issue_S(sn);
-          umma_commit(&k_empty[sn]);
-        }
-        mbar_wait_quiet(&v_full[s], ph);
-        mbar_wait_quiet(p_full, j & 1);
-        tc_fence_after();
-        issue_PV(s, j);
-        umma_commit(&v_empty[s]);
-        s = sn;
-        ph = phn;
-        if (++sn == NS) {
-          sn = 0;
-          phn ^= 1;
+          issue_PV(s, j);
+          umma_commit(&v_empty[s]);
+          s = sn;
+          ph = phn;
+          if (++sn == NS) {
+            sn = 0;
+            phn ^= 1;
+          }
         }
       }
     }
@@ -212,16 +235,20 @@ attn1_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
     reg_alloc<208>();
     const int quarter = warp & 3;
     const int r = quarter * 32 + lane;
-    const int qrow = q0 + r;
     const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
     const uint32_t tS = tmem_base + lane_off;
     const uint32_t tP = tmem_base + 128 + lane_off;
     const uint32_t tO = tmem_base + 192 + lane_off;
+    uint32_t it = 0;
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+    const int bh = item / p.q_tiles;
+    const int qrow = (item - bh * p.q_tiles) * 128 + r;
+    const int head = bh % p.heads, bz = bh / p.heads;
     float m_used = -INFINITY;
     float l = 0.f;
-    for (int j = 0; j < nkv; ++j) {
+    for (int j = 0; j < nkv; ++j, ++it) {
       const int kv_valid = min(128, p.nkv - j * 128);
-      mbar_wait_quiet(s_full, j & 1);
+      mbar_wait_quiet(s_full, it & 1);
       tc_fence_after();
       uint32_t raw[128];
       tmem_ld32(tS, raw);
@@ -274,7 +301,7 @@ attn1_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
             continue;
           }
           if (c == OVG_ATT_LATE_WAIT) {
-            mbar_wait_quiet(o_ready, (j - 1) & 1);   // PV(j-1) complete: P buffer reusable, O stable
+            mbar_wait_quiet(o_ready, (it - 1) & 1);   // PV(j-1) complete: P buffer reusable, O stable
             tc_fence_after();
 #pragma unroll
             for (int h = 0; h < OVG_ATT_LATE_WAIT; ++h) tmem_st16(tP + h * 16, held + h * 16);
@@ -345,15 +372,18 @@ attn1_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
       if (lane == 0) mbar_arrive(p_full);
     }
     // ---- epilogue: O / l -> bf16 -> out[b, qrow, head*64 .. +64)
-    mbar_wait_quiet(o_ready, (nkv - 1) & 1);
+    mbar_wait_quiet(o_ready, (it - 1) & 1);
     tc_fence_after();
     const float inv = 1.0f / l;
     uint32_t o[64];
     tmem_ld32(tO, o);
     tmem_ld32(tO + 32, o + 32);
     tmem_ld_wait();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(o_taken);             // the next item's first PV may overwrite O
     if (qrow < p.n) {
-      uint4* dst = reinterpret_cast<uint4*>(p.out + (static_cast<long long>(blockIdx.z) * p.n + qrow) * p.C + head * 64);
+      uint4* dst = reinterpret_cast<uint4*>(p.out + (static_cast<long long>(bz) * p.n + qrow) * p.C + head * 64);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         uint4 w;
@@ -364,6 +394,7 @@ attn1_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
         dst[i] = w;
       }
     }
+    }   // work items
   }
   tc_fence_before();
   __syncthreads();
