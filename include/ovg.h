@@ -97,6 +97,13 @@ int ovg_attention(const void* q, const void* k, const void* v, void* out, int ba
  * out [batch, nq, heads*64] (context parallelism: a rank's own queries against the keys / values of all ranks). */
 int ovg_attention_kv(const void* q, const void* k, const void* v, void* out, int batch, int heads, int nq, int nkv,
                      void* stream);
+/* Same with a scratch buffer of ovg_attention_scratch_bytes() bytes (16-byte aligned): for long sequences whose 128-row query tiles
+ * do not fill the last wave of resident CTAs (two per SM), the tiles of that wave are cut into 2-4 key ranges, one CTA each, and
+ * a small kernel merges their (un-normalised O, softmax reference, row sum) -- e.g. 1 376 tiles on 296 slots: 4.67 instead of 5
+ * waves.  Results are deterministic (fixed merge order); scratch NULL = no split. */
+long long ovg_attention_scratch_bytes(void);
+int ovg_attention_kv_ws(const void* q, const void* k, const void* v, void* out, int batch, int heads, int nq, int nkv,
+                        void* scratch, long long scratch_bytes, void* stream);
 
 /* LayerNorm over the last dim, fp32 or bf16 in -> bf16 (out_is_f32 = 0), fp32 (1) or fp16 (2) out, optional affine, optional row gather
  * (out row m <- in row (m / grp_out) * grp_in + grp_off + m % grp_out; grp_out = 0: identity).

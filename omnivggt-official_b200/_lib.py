@@ -99,6 +99,8 @@ EXPORTS = {
     "ovg_gemm": (C.c_int, [C.POINTER(GemmArgs), _vp]),
     "ovg_attention": (C.c_int, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "ovg_attention_kv": (C.c_int, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "ovg_attention_scratch_bytes": (C.c_longlong, []),
+    "ovg_attention_kv_ws": (C.c_int, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _ll, _vp]),
     "ovg_peer_barrier": (C.c_int, [C.POINTER(_vp), _vp, _i, _i, _vp]),
     "ovg_aggregator_forward_cp": (C.c_int, [_vp, C.POINTER(ContextParallelDesc), _vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _vp, _vp, _i,
                                             _i, _i, _i, _vp, _ll, _pp, _vp, _vp]),

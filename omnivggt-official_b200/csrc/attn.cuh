@@ -21,7 +21,11 @@ struct AttnParams {
   __nv_bfloat16* out;  // [batch, n, C]
   long long* prof;     // optional [2][8] cycle counters (OVG_ATT_PROFILE builds only)
   int q_tiles;         // ceil(n / 128)
-  int items;           // batch * heads * q_tiles work items, walked by the persistent grid (item = bh * q_tiles + q tile)
+  int items;           // work items: (batch, head, q tile) tiles -- item = bh * q_tiles + q tile -- walked by the persistent grid, or,
+                       // with parts > 1 (one CTA per item), n_full whole tiles followed by the LAST tiles cut into `parts` KV ranges
+  int n_full, parts;   // parts <= 1: no split
+  float* part_o;       // [(tile - n_full) * parts + part][128][64] un-normalised O of a KV range
+  float2* part_ml;     // ... [128] (softmax reference, row sum) of that range; attn_merge_kernel combines them
 };
 #ifdef OVG_ATT_PROFILE
 #define ATT_T(var) const long long var = clock64()
@@ -104,7 +108,18 @@ attn1_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int nkv = (p.nkv + 127) / 128;
+  // KV tile range [jb, jb + nkv) of this CTA's work items: everything, or -- tail tiles of a long sequence, one CTA per item --
+  // one of `parts` ranges whose partial results attn_merge_kernel combines (fills the last, partly empty wave of CTAs).
+  // Every role derives what it needs from blockIdx when it needs it (nothing of this stays live across the softmax loop).
+  const bool is_part = p.parts > 1 && static_cast<int>(blockIdx.x) >= p.n_full;
+  auto part_of = [&]() { const int i = blockIdx.x - p.n_full; return i - (i / p.parts) * p.parts; };
+  auto split_tile_of = [&]() { return p.n_full + static_cast<int>(blockIdx.x - p.n_full) / p.parts; };
+  int nkv = (p.nkv + 127) / 128, jb = 0;
+  if (is_part) {
+    const int part = part_of();
+    jb = part * nkv / p.parts;
+    nkv = (part + 1) * nkv / p.parts - jb;
+  }
 
   if (warp == 0 && lane == 0) {
     if (smem_u32(smem) & 1023u) {
@@ -145,17 +160,18 @@ attn1_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
       int s = 0;
       uint32_t ph = 0, iph = 0;
       for (int item = blockIdx.x; item < p.items; item += gridDim.x, iph ^= 1) {
-        const int bh = item / p.q_tiles, q0 = (item - bh * p.q_tiles) * 128;
+        const int tile = is_part ? split_tile_of() : item;
+        const int bh = tile / p.q_tiles, q0 = (tile - bh * p.q_tiles) * 128;
         mbar_wait_quiet(q_empty, iph ^ 1);          // (first item: passes) the previous item's last S MMA has been issued
         mbar_expect_tx(q_full, ATT_TILE_BYTES);
         tma_load_3d(sQ, &tmQ, q_full, 0, q0, bh);
         for (int j = 0; j < nkv; ++j) {
           mbar_wait_quiet(&k_empty[s], ph ^ 1);
           mbar_expect_tx(&k_full[s], ATT_TILE_BYTES);
-          tma_load_3d(sK + s * ATT_TILE_BYTES, &tmK, &k_full[s], 0, j * 128, bh);
+          tma_load_3d(sK + s * ATT_TILE_BYTES, &tmK, &k_full[s], 0, (jb + j) * 128, bh);
           mbar_wait_quiet(&v_empty[s], ph ^ 1);
           mbar_expect_tx(&v_full[s], ATT_TILE_BYTES);
-          tma_load_3d(sV + s * ATT_TILE_BYTES, &tmV, &v_full[s], 0, j * 128, bh);
+          tma_load_3d(sV + s * ATT_TILE_BYTES, &tmV, &v_full[s], 0, (jb + j) * 128, bh);
           if (++s == NS) {
             s = 0;
             ph ^= 1;
@@ -241,13 +257,15 @@ attn1_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
     const uint32_t tO = tmem_base + 192 + lane_off;
     uint32_t it = 0;
     for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
-    const int bh = item / p.q_tiles;
-    const int qrow = (item - bh * p.q_tiles) * 128 + r;
+    const int tile = is_part ? split_tile_of() : item;
+    const int bh = tile / p.q_tiles;
+    const int qrow = (tile - bh * p.q_tiles) * 128 + r;
+    const int kv_rem = p.nkv - jb * 128;           // keys from this item's first KV tile to the end of the sequence
     const int head = bh % p.heads, bz = bh / p.heads;
     float m_used = -INFINITY;
     float l = 0.f;
     for (int j = 0; j < nkv; ++j, ++it) {
-      const int kv_valid = min(128, p.nkv - j * 128);
+      const int kv_valid = min(128, kv_rem - j * 128);
       mbar_wait_quiet(s_full, it & 1);
       tc_fence_after();
       uint32_t raw[128];
@@ -382,7 +400,14 @@ attn1_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(o_taken);             // the next item's first PV may overwrite O
-    if (qrow < p.n) {
+    if (is_part) {         // one KV range of a split tile: un-normalised O, reference and row sum for attn_merge_kernel
+      const long long sidx = static_cast<long long>(blockIdx.x) - p.n_full;     // == (tile - n_full) * parts + part
+      float4* dst = reinterpret_cast<float4*>(p.part_o + (sidx * 128 + r) * 64);
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        dst[i] = make_float4(__uint_as_float(o[4 * i]), __uint_as_float(o[4 * i + 1]), __uint_as_float(o[4 * i + 2]), __uint_as_float(o[4 * i + 3]));
+      p.part_ml[sidx * 128 + r] = make_float2(m_used, l);
+    } else if (qrow < p.n) {
       uint4* dst = reinterpret_cast<uint4*>(p.out + (static_cast<long long>(bz) * p.n + qrow) * p.C + head * 64);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
@@ -404,6 +429,46 @@ attn1_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
   }
 }
 
-
+// Combine the KV ranges of the split tiles: out = sum_i 2^(m_i - M) O_i / sum_i 2^(m_i - M) l_i, M = max_i m_i (fixed order of the
+// parts: deterministic).  One block per split tile, one thread per query row.
+__global__ void __launch_bounds__(128) attn_merge_kernel(const AttnParams p) {
+  const int tile = p.n_full + blockIdx.x, r = threadIdx.x;
+  const int bh = tile / p.q_tiles;
+  const int qrow = (tile - bh * p.q_tiles) * 128 + r;
+  if (qrow >= p.n) return;
+  const int head = bh % p.heads, bz = bh / p.heads;
+  const long long s0 = static_cast<long long>(blockIdx.x) * p.parts;
+  float M = -INFINITY;
+  for (int i = 0; i < p.parts; ++i) M = fmaxf(M, p.part_ml[(s0 + i) * 128 + r].x);
+  float acc[64];
+#pragma unroll
+  for (int c = 0; c < 64; ++c) acc[c] = 0.f;
+  float L = 0.f;
+  for (int i = 0; i < p.parts; ++i) {
+    const float2 ml = p.part_ml[(s0 + i) * 128 + r];
+    const float w = exp2f(ml.x - M);
+    L = fmaf(w, ml.y, L);
+    const float4* o4 = reinterpret_cast<const float4*>(p.part_o + ((s0 + i) * 128 + r) * 64);
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+      const float4 t = o4[c];
+      acc[4 * c] = fmaf(w, t.x, acc[4 * c]);
+      acc[4 * c + 1] = fmaf(w, t.y, acc[4 * c + 1]);
+      acc[4 * c + 2] = fmaf(w, t.z, acc[4 * c + 2]);
+      acc[4 * c + 3] = fmaf(w, t.w, acc[4 * c + 3]);
+    }
+  }
+  const float inv = 1.0f / L;
+  uint4* dst = reinterpret_cast<uint4*>(p.out + (static_cast<long long>(bz) * p.n + qrow) * p.C + head * 64);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    uint4 w;
+    w.x = pack_bf16(acc[8 * i + 0] * inv, acc[8 * i + 1] * inv);
+    w.y = pack_bf16(acc[8 * i + 2] * inv, acc[8 * i + 3] * inv);
+    w.z = pack_bf16(acc[8 * i + 4] * inv, acc[8 * i + 5] * inv);
+    w.w = pack_bf16(acc[8 * i + 6] * inv, acc[8 * i + 7] * inv);
+    dst[i] = w;
+  }
+}
 
 }  // namespace ovg

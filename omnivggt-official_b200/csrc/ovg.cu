@@ -427,8 +427,10 @@ int ovg_gemm(const ovg_gemm_args* a, void* stream) {
   }
 }
 
-int ovg_attention_kv(const void* q, const void* k, const void* v, void* out, int batch, int heads, int nq, int nkv,
-                     void* stream) {
+long long ovg_attention_scratch_bytes(void) { return 2LL * 2 * num_sms() * 128 * (64 * 4 + 8) + 256; }
+
+int ovg_attention_kv_ws(const void* q, const void* k, const void* v, void* out, int batch, int heads, int nq, int nkv,
+                        void* scratch, long long scratch_bytes, void* stream) {
   OVG_REQUIRE(q && k && v && out, "null operand");
   OVG_REQUIRE(batch > 0 && heads > 0 && nq > 0 && nkv > 0, "empty problem");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -447,21 +449,59 @@ int ovg_attention_kv(const void* q, const void* k, const void* v, void* out, int
     once.mark_done();
   }
   const int q_tiles = (nq + 127) / 128;
-  const long long items = static_cast<long long>(q_tiles) * heads * batch;
-  OVG_REQUIRE(items < (1LL << 30), "too many tiles");
-  ovg::AttnParams p{nq, nkv, heads, heads * 64, reinterpret_cast<__nv_bfloat16*>(out), g_attn_prof, q_tiles, static_cast<int>(items)};
+  const long long tiles = static_cast<long long>(q_tiles) * heads * batch;
+  OVG_REQUIRE(tiles < (1LL << 28), "too many tiles");
+  ovg::AttnParams p{nq, nkv, heads, heads * 64, reinterpret_cast<__nv_bfloat16*>(out), g_attn_prof, q_tiles, static_cast<int>(tiles),
+                    static_cast<int>(tiles), 1, nullptr, nullptr};
 #ifndef OVG_ATT_PERSISTENT
 #define OVG_ATT_PERSISTENT 1    // 0: always one CTA per work item (A/B builds)
+#endif
+#ifndef OVG_ATT_SPLIT_TAIL
+#define OVG_ATT_SPLIT_TAIL 1    // 0: never split the tiles of the last wave over the keys (A/B builds)
 #endif
   // Short sequences (frame / DINOv2 attention: 11 KV tiles per item): two resident CTAs per SM walk the items, so barrier /
   // TMEM set-up is paid once and the next item's Q, K, V stream in under the current item's tail (0.1126 -> 0.1085 ms at
   // 8 x 16 x 1374).  Long sequences keep one CTA per item: the hardware's dynamic CTA placement balances the 4.65 "waves" of
   // the global attention better than a static round robin (0.619 vs 0.649 ms), profiles/r02_attn_ab.jsonl.
   const int resident = 2 * num_sms();
-  const bool persistent = OVG_ATT_PERSISTENT && items > resident && (nkv + 127) / 128 <= 16;
-  const int grid1 = persistent ? resident : static_cast<int>(items);
+  const int kv_tiles = (nkv + 127) / 128;
+  const bool persistent = OVG_ATT_PERSISTENT && tiles > resident && kv_tiles <= 16;
+  // Long sequences: the tiles of the last, partly empty wave are cut into 2-4 KV ranges (one CTA each, issued after the whole
+  // tiles) whose partial (O, reference, row sum) a small kernel merges: 1 376 tiles on 296 slots cost 4.67 instead of 5 waves.
+  int parts = 1;
+  const int tail = static_cast<int>(tiles % resident);
+  if (OVG_ATT_SPLIT_TAIL && !persistent && scratch && tiles > resident && tail > 0 && kv_tiles >= 24) {
+    double best = 1.0;
+    for (int c = 2; c <= 4; ++c) {
+      const double cost = static_cast<double>((static_cast<long long>(tail) * c + resident - 1) / resident) / c + 0.04;   // + merge
+      if (cost < best - 0.1) {
+        best = cost;
+        parts = c;
+      }
+    }
+    if (parts > 1) {
+      const long long need = static_cast<long long>(tail) * parts * 128 * (64 * 4 + 8);
+      if (need > scratch_bytes - 256 || (reinterpret_cast<uintptr_t>(scratch) & 15)) parts = 1;
+    }
+  }
+  if (parts > 1) {
+    p.n_full = static_cast<int>(tiles) - tail;
+    p.parts = parts;
+    p.items = p.n_full + tail * parts;
+    p.part_o = static_cast<float*>(scratch);
+    p.part_ml = reinterpret_cast<float2*>(p.part_o + static_cast<long long>(tail) * parts * 128 * 64);
+  }
+  const int grid1 = persistent ? resident : p.items;
   ovg::attn1_kernel<<<grid1, ovg::ATT1_THREADS, ovg::ATT1_SMEM_BYTES, st>>>(tq, tk, tv, p);
-  return post_launch("ovg_attention");
+  rc = post_launch("ovg_attention");
+  if (rc || parts <= 1) return rc;
+  ovg::attn_merge_kernel<<<tail, 128, 0, st>>>(p);
+  return post_launch("ovg_attention(merge)");
+}
+
+int ovg_attention_kv(const void* q, const void* k, const void* v, void* out, int batch, int heads, int nq, int nkv,
+                     void* stream) {
+  return ovg_attention_kv_ws(q, k, v, out, batch, heads, nq, nkv, nullptr, 0, stream);
 }
 
 int ovg_attention(const void* q, const void* k, const void* v, void* out, int batch, int heads, int n, void* stream) {

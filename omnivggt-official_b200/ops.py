@@ -89,12 +89,21 @@ def qkv_proj(a, w, bias, qn_w, qn_b, kn_w, kn_b, q, k, v, *, ntok, T, nspecial=0
          qscale=(1.0 / math.sqrt(64.0)) * math.log2(math.e), block_n=block_n)
 
 
-def attention(q, k, v, out, batch: int, heads: int, n: int):
+def attention(q, k, v, out, batch: int, heads: int, n: int, scratch=None):
+    """scratch: uint8 buffer of ovg_attention_scratch_bytes() -> long sequences may split the tiles of the last CTA wave over the keys."""
     for t, nm in ((q, "q"), (k, "k"), (v, "v"), (out, "out")):
         _chk(t, BF16, nm)
         assert t.is_contiguous()
-    L.check(L.lib().ovg_attention(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), batch, heads, n, L.stream()))
+    if scratch is None:
+        L.check(L.lib().ovg_attention(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), batch, heads, n, L.stream()))
+    else:
+        L.check(L.lib().ovg_attention_kv_ws(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), batch, heads, n, n,
+                                            scratch.data_ptr(), scratch.numel(), L.stream()))
     return out
+
+
+def attention_scratch(device):
+    return torch.empty(L.lib().ovg_attention_scratch_bytes(), device=device, dtype=torch.uint8)
 
 
 def attention_kv(q, k, v, out, batch: int, heads: int, nq: int, nkv: int):

@@ -195,6 +195,35 @@ def test_attention_global_sizes_of_baseline_configs(heads, n):
     ops.attention(qs, kb, vb, out2, 1, heads, n)
     torch.cuda.synchronize()
     assert torch.equal(out, out2)          # run-to-run bit-identical (no atomics, no ordering races)
+    # with scratch the tiles of the last CTA wave are split over the keys and merged (ovg_attention_kv_ws): same bar, deterministic
+    scratch = ops.attention_scratch("cuda")
+    out3, out4 = torch.zeros_like(out), torch.zeros_like(out)
+    ops.attention(qs, kb, vb, out3, 1, heads, n, scratch=scratch)
+    ops.attention(qs, kb, vb, out4, 1, heads, n, scratch=scratch)
+    torch.cuda.synchronize()
+    e3 = rel(out3, ref)
+    print(f"attention n={n} (split tail): rel-L2 {e3:.3e}, vs unsplit {rel(out3, out):.3e}")
+    assert e3 < 1e-2 and torch.equal(out3, out4) and rel(out3, out) < 4e-3
+
+
+@pytest.mark.parametrize("batch,heads,n", [(1, 16, 4 * 1374), (2, 16, 5 * 1374), (1, 7, 9000)])
+def test_attention_split_tail_shapes(batch, heads, n):
+    """KV-split tail tiles at other tile counts (688 / 1 728 / 497 tiles on 296 resident CTAs), ragged last KV tile, peaky rows."""
+    ops = _ops()
+    q = randn(batch, heads, n, 64, seed=1) * 1.5
+    k = randn(batch, heads, n, 64, seed=2)
+    v = randn(batch, heads, n, 64, seed=3)
+    k[:, :, n - 3] *= 6.0                    # a late dominant key: the parts end on very different references
+    qs = (q * (math.log2(math.e) / 8.0)).to(BF16)
+    kb, vb = k.to(BF16), v.to(BF16)
+    del q, k, v
+    scratch = ops.attention_scratch("cuda")
+    out = torch.zeros(batch, n, heads * 64, device="cuda", dtype=BF16)
+    ops.attention(qs, kb, vb, out, batch, heads, n, scratch=scratch)
+    ref = _sdpa_fp32_chunked(qs, kb, vb)
+    torch.cuda.synchronize()
+    assert torch.isfinite(out.float()).all()
+    assert rel(out, ref) < 1e-2, rel(out, ref)
 
 
 def test_attention_peaky_rows_rescale():

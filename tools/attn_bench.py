@@ -34,8 +34,9 @@ def timeit(fn, iters=7, warm=2):
 
 
 res = {"tag": sys.argv[1] if len(sys.argv) > 1 else "", "lib": os.environ.get("OVG_LIB_PATH", "libovg.so"),
-       }
-shapes = {"global8": (1, 16, 8 * 1374), "frame8": (8, 16, 1374), "global24": (1, 16, 24 * 1374)}
+       "split_tail": os.environ.get("ATTN_SPLIT", "1") != "0"}
+shapes = {"global8": (1, 16, 8 * 1374), "frame8": (8, 16, 1374), "global24": (1, 16, 24 * 1374), "global4": (1, 16, 4 * 1374)}
+scratch = ops.attention_scratch("cuda") if os.environ.get("ATTN_SPLIT", "1") != "0" else None     # KV-split tail tiles (ovg_attention_kv_ws)
 if os.environ.get("ATTN_SHAPES"):
     shapes = {k: shapes[k] for k in os.environ["ATTN_SHAPES"].split(",")}
 for name, (b, h, n) in shapes.items():
@@ -44,7 +45,7 @@ for name, (b, h, n) in shapes.items():
     k = torch.randn(b, h, n, 64, device="cuda", generator=g).to(BF16)
     v = torch.randn(b, h, n, 64, device="cuda", generator=g).to(BF16)
     o = torch.empty(b, n, h * 64, device="cuda", dtype=BF16)
-    ms = timeit(lambda: ops.attention(q, k, v, o, b, h, n), iters=5 if n > 20000 else 7)
+    ms = timeit(lambda: ops.attention(q, k, v, o, b, h, n, scratch=scratch), iters=5 if n > 20000 else 7)
     fl = 4.0 * b * h * n * n * 64
     res[name] = dict(ms=round(ms, 4), tflops=round(fl / ms / 1e9, 1))
     if os.environ.get("ATTN_SDPA", "1") != "0":
@@ -53,11 +54,11 @@ for name, (b, h, n) in shapes.items():
         # value check against the library kernel (q carries log2(e)/8; SDPA gets the matching natural-log scale)
         ref = F.scaled_dot_product_attention(q.float() if n < 3000 else q, k.float() if n < 3000 else k,
                                              v.float() if n < 3000 else v, scale=0.6931471805599453).transpose(1, 2).reshape(b, n, h * 64)
-        ops.attention(q, k, v, o, b, h, n)
+        ops.attention(q, k, v, o, b, h, n, scratch=scratch)
         torch.cuda.synchronize()
         res[name]["rel_l2_vs_sdpa"] = round(((o.float() - ref.float()).norm() / ref.float().norm()).item(), 5)
         o2 = torch.empty_like(o)
-        ops.attention(q, k, v, o2, b, h, n)
+        ops.attention(q, k, v, o2, b, h, n, scratch=scratch)
         torch.cuda.synchronize()
         res[name]["bit_identical_rerun"] = bool(torch.equal(o, o2))
 print(json.dumps(res))
