@@ -343,6 +343,11 @@ int ovg_aggregator_forward_cp(ovg_aggregator* h, const ovg_context_parallel* cp,
 /* Timing hook for bench.py: when enabled, every global-attention launch of ovg_aggregator_forward is bracketed by CUDA events
  * on its stream; after a synchronize, ovg_runtime_attention_times() returns the elapsed ms of the launches since the enable. */
 void ovg_runtime_time_attention(int enable);
+/* Process-wide switch (default on): the block runtimes hand ovg_attention_kv_ws their scratch, so long sequences may split the
+ * tiles of the last CTA wave over the keys.  Off: every tile is computed by one CTA -- the summation order of a tile then does not
+ * depend on how many tiles the launch has, which is what makes a context-parallel forward BIT-identical to the single-GPU one
+ * (tests/test_cp_gpu.py checks that with the switch off, and agreement within 5e-3 of the dense outputs with it on). */
+void ovg_runtime_attention_split(int enable);
 int ovg_runtime_attention_times(float* ms, int max_n);
 
 #ifdef __cplusplus

@@ -139,6 +139,7 @@ EXPORTS = {
     "ovg_camera_workspace_bytes": (_ll, [_vp, _i]),
     "ovg_camera_forward": (C.c_int, [_vp, _vp, _i, _i, _i, _vp, _vp, _ll, _vp]),
     "ovg_runtime_time_attention": (None, [_i]),
+    "ovg_runtime_attention_split": (None, [_i]),
     "ovg_runtime_attention_times": (C.c_int, [_vp, _i]),
 }
 PERCENTILE_WORKSPACE_BYTES = 6 * 8 + 512 * 4 + 4 * 4
