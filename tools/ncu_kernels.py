@@ -1,6 +1,7 @@
 """The block-level kernels at cfg2 shapes, one launch each inside a cudaProfiler range (for `ncu --set full`):
    0 qkv fused (LN + RoPE epilogue)   1 proj (residual)   2 fc1 (GELU)   3 fc2 (residual)   4 global attention   5 layernorm
    6 DPT tail (3x3 conv 128->32 + 1x1 + activations, 8 frames @ 518^2)   7 bilinear upsampling 296^2 -> 518^2 (128 ch)
+   (6 + 7 = the two-kernel tail; the product runs the fused tail:)   7b tail_tables + fusedtail_kernel (fp16)   4b frame attention
 and the modality gather / scatter kernels at the cfg5 shapes (24 views, 6 depth views):
    8 assemble_tokens   9 inject_snapshot (with bf16 slot)   10 depth_stats   11 depth_im2col   12 image_im2col
 NCU_ONLY=attn restricts the profiled range to the global attention.
@@ -72,6 +73,14 @@ scratch5 = torch.zeros(ops.L.DEPTH_SCRATCH_DOUBLES(1), dtype=torch.float64, devi
 cols5 = torch.empty(len(didx) * P5, 392, device=dev, dtype=BF16)
 img5 = torch.rand(K5, 3, 518, 518, device=dev, generator=g)
 icol5 = torch.empty(K5 * P5, 592, device=dev, dtype=BF16)
+xs16, wt16 = xs.to(torch.float16), wt.to(torch.float16)
+qf = (torch.randn(8, 16, T, 64, device=dev, generator=g) * 0.18).to(BF16)
+kf, vf = torch.randn_like(qf), torch.randn_like(qf)
+of = torch.empty(8, T, C, device=dev, dtype=BF16)
+att_scratch = ops.attention_scratch(dev)
+q.copy_((torch.randn(1, 16, M, 64, device=dev, generator=g) * 0.18).to(BF16))
+k.copy_(torch.randn(1, 16, M, 64, device=dev, generator=g).to(BF16))
+v.copy_(torch.randn(1, 16, M, 64, device=dev, generator=g).to(BF16))
 ONLY = os.environ.get("NCU_ONLY", "")
 
 
@@ -97,6 +106,9 @@ def run_blocks():
     ops.gemm(xt.reshape(-1, 128), wt, taps=taps, epi=ops.L.EPI_HEADTAIL, bias=bt, w2=w2t, b2=b2t, outc=4, head_act=1,
              preds=preds, conf=conf, rowmap=ops.L.ROWS_PAD, gh=hh, gw=ww)
     ops.upsample_bilinear(xs, xu, tx, ty, Fr, 296, 296, hh, ww, 128)
+    ops.dpt_tail(xs16, tx, ty, wt16, bt, w2t, b2t, 1, Fr, 296, 296, hh, ww)
+    ops.attention(qf, kf, vf, of, 8, 16, T)
+    ops.attention(q, k, v, o, 1, 16, M, scratch=att_scratch)       # global attention with the KV-split tail tiles + merge
 
 
 for _ in range(2):
