@@ -427,7 +427,7 @@ int ovg_gemm(const ovg_gemm_args* a, void* stream) {
   }
 }
 
-long long ovg_attention_scratch_bytes(void) { return 2LL * 2 * num_sms() * 128 * (64 * 4 + 8) + 256; }
+long long ovg_attention_scratch_bytes(void) { return 4LL * 2 * num_sms() * 128 * (64 * 4 + 8) + 256; }   // <= 4 parts of < one wave of tiles
 
 int ovg_attention_kv_ws(const void* q, const void* k, const void* v, void* out, int batch, int heads, int nq, int nkv,
                         void* scratch, long long scratch_bytes, void* stream) {
