@@ -64,7 +64,8 @@ __device__ __forceinline__ float2 exp2_poly2(float2 x) {
 #define OVG_ATT_LATE_WAIT 1   // P chunks computed before the wait for PV(j-1) (0: wait before the first store, as in round 1)
 #endif
 #ifndef OVG_ATT_EMU_PAIRS
-#define OVG_ATT_EMU_PAIRS 4   // of every 16 element pairs, how many take the polynomial path (0..4; 4 measured best)
+#define OVG_ATT_EMU_PAIRS 2   // of every 16 element pairs, how many take the polynomial path (0..4): 4 is fastest for the isolated
+                              // kernel (603 us), 2 inside the power-capped forward (profiles/r02_attn_step_ab.txt)
 #endif
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
