@@ -65,7 +65,7 @@ __device__ __forceinline__ float2 exp2_poly2(float2 x) {
 #endif
 #ifndef OVG_ATT_EMU_PAIRS
 #define OVG_ATT_EMU_PAIRS 2   // of every 16 element pairs, how many take the polynomial path (0..4): 4 is fastest for the isolated
-                              // kernel (603 us), 2 inside the power-capped forward (profiles/r02_attn_step_ab.txt)
+                              // kernel (603 us), 2 inside the power-capped forward (profiles/r02_step_ab.txt)
 #endif
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;

@@ -759,7 +759,10 @@ headtail_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 constexpr int GEMM2_STG_BYTES = 8 * 4096;   // one 32 x 32 fp32 (or bf16) staging tile per epilogue warp; followed by the QKV tables
 template <int BN>
 struct Gemm2Cfg {
-  static constexpr int STAGES = BN >= 256 ? 5 : 7;
+#ifndef OVG_GEMM2_STAGES
+#define OVG_GEMM2_STAGES 5
+#endif
+  static constexpr int STAGES = BN >= 256 ? OVG_GEMM2_STAGES : 7;
   static constexpr int B_BYTES = (BN / 2) * GEMM_BK * 2;       // each CTA stages half of the B rows
   static constexpr int STAGE_BYTES = GEMM_A_BYTES + B_BYTES;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + 1024 + GEMM2_STG_BYTES + GEMM_QKV_TABLE_BYTES;

@@ -199,7 +199,10 @@ int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap
   const int grid = 2 * (tiles < pairs ? tiles : pairs);
   // last partial wave as half tiles when both halves of every leftover tile find a free cluster (gemm.cuh)
   const int tail = tiles > pairs ? tiles % pairs : 0;
-  p.split_tail = (BN == 256 && tail > 0 && 2 * tail <= pairs) ? 1 : 0;
+#ifndef OVG_GEMM_SPLIT_TAIL
+#define OVG_GEMM_SPLIT_TAIL 1
+#endif
+  p.split_tail = (OVG_GEMM_SPLIT_TAIL && BN == 256 && tail > 0 && 2 * tail <= pairs) ? 1 : 0;
   kern<<<grid, ovg::GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, tbh, to[0], to[1], to[2], p);
   return post_launch("ovg_gemm(2sm)");
 }
@@ -518,7 +521,10 @@ int ovg_layernorm(const void* in, int in_is_bf16, long long ld_in, void* out, in
   ovg::LnParams p{in, in_is_bf16, ld_in, out, out_is_f32, ld_out, rows, C, w, b, eps,
                   grp_out, grp_in, grp_off};
   constexpr int ln_threads = 256;     // 8 rows per block
-  constexpr int ln_persist = 2;       // persistent grid: blocks per SM
+#ifndef OVG_LN_PERSIST
+#define OVG_LN_PERSIST 2
+#endif
+  constexpr int ln_persist = OVG_LN_PERSIST;       // persistent grid: blocks per SM
   OVG_REQUIRE((reinterpret_cast<uintptr_t>(w) & 15) == 0 && (reinterpret_cast<uintptr_t>(b) & 15) == 0, "w / b must be 16-byte aligned");
   const int rpb = ln_threads / 32;
   int blocks = (rows + rpb - 1) / rpb;
