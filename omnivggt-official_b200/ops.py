@@ -106,12 +106,13 @@ def attention_scratch(device):
     return torch.empty(L.lib().ovg_attention_scratch_bytes(), device=device, dtype=torch.uint8)
 
 
-def attention_kv(q, k, v, out, batch: int, heads: int, nq: int, nkv: int):
+def attention_kv(q, k, v, out, batch: int, heads: int, nq: int, nkv: int, scratch=None):
     """q [batch, heads, nq, 64] against k, v [batch, heads, nkv, 64] -> out [batch, nq, heads*64]."""
     for t, nm in ((q, "q"), (k, "k"), (v, "v"), (out, "out")):
         _chk(t, BF16, nm)
         assert t.is_contiguous()
-    L.check(L.lib().ovg_attention_kv(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), batch, heads, nq, nkv, L.stream()))
+    L.check(L.lib().ovg_attention_kv_ws(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), batch, heads, nq, nkv,
+                                        L.ptr(scratch), 0 if scratch is None else scratch.numel(), L.stream()))
     return out
 
 

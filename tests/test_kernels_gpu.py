@@ -206,9 +206,10 @@ def test_attention_global_sizes_of_baseline_configs(heads, n):
     assert e3 < 1e-2 and torch.equal(out3, out4) and rel(out3, out) < 4e-3
 
 
-@pytest.mark.parametrize("batch,heads,n", [(1, 16, 4 * 1374), (2, 16, 5 * 1374), (1, 7, 9000)])
+@pytest.mark.parametrize("batch,heads,n", [(1, 16, 4 * 1374), (2, 16, 4 * 1374), (1, 7, 9000)])
 def test_attention_split_tail_shapes(batch, heads, n):
-    """KV-split tail tiles at other tile counts (688 / 1 728 / 497 tiles on 296 resident CTAs), ragged last KV tile, peaky rows."""
+    """KV-split tail tiles at other tile counts (688 / 1 376 over two batch entries / 497 tiles on 296 resident CTAs), ragged last KV
+    tile, peaky rows."""
     ops = _ops()
     q = randn(batch, heads, n, 64, seed=1) * 1.5
     k = randn(batch, heads, n, 64, seed=2)
@@ -621,6 +622,18 @@ def test_attention_kv_own_queries_against_all_keys():
     ops.attention_kv(q[:, :, lo:hi].contiguous(), k, v, part, 1, heads, hi - lo, n)
     torch.cuda.synchronize()
     assert torch.equal(part, full[:, lo:hi])
+    # the shape a rank of a 2-GPU context-parallel forward runs (half of the query rows of 8 views against all keys): 688 tiles,
+    # the 96 of the last wave split over the keys
+    heads, n = 16, 8 * 1374
+    q = randn(1, heads, n // 2, 64, seed=4, dtype=BF16) * 0.18
+    k = randn(1, heads, n, 64, seed=5, dtype=BF16)
+    v = randn(1, heads, n, 64, seed=6, dtype=BF16)
+    plain = torch.zeros(1, n // 2, heads * 64, device="cuda", dtype=BF16)
+    split = torch.zeros_like(plain)
+    ops.attention_kv(q, k, v, plain, 1, heads, n // 2, n)
+    ops.attention_kv(q, k, v, split, 1, heads, n // 2, n, scratch=ops.attention_scratch("cuda"))
+    torch.cuda.synchronize()
+    assert not torch.equal(plain, split) and rel(split, plain) < 4e-3
 
 
 def test_qkv_epilogue_stores_kv_rows_into_peer_buffers():
