@@ -178,9 +178,9 @@ struct InjectParams {
 };
 
 __global__ void inject_snapshot_kernel(const InjectParams p) {
-  const int row = blockIdx.x;
+  // with a snapshot slot: one block per token row; without: only the camera-token rows change (one block per frame)
+  const int row = p.slot ? blockIdx.x : blockIdx.x * p.T;
   const int k = row / p.T, t = row % p.T;
-  if (!p.slot && t != 0) return;
   for (int c = threadIdx.x * 4; c < p.C; c += blockDim.x * 4) {
     float4 v = *reinterpret_cast<const float4*>(p.x + static_cast<long long>(row) * p.C + c);
     if (t == 0) {

@@ -570,7 +570,7 @@ int ovg_inject_snapshot(float* x, const float* inj, void* slot, float* cam_out, 
   OVG_REQUIRE(coff == 0 || coff == C, "coff must be 0 or C");
   ovg::InjectParams p{x, inj, reinterpret_cast<__nv_bfloat16*>(slot), cam_out, K, T, C, coff};
   const int threads = C / 4 < 256 ? ((C / 4 + 31) / 32) * 32 : 256;
-  ovg::inject_snapshot_kernel<<<K * T, threads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  ovg::inject_snapshot_kernel<<<slot ? K * T : K, threads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
   return post_launch("ovg_inject_snapshot");
 }
 
