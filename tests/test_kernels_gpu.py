@@ -303,6 +303,12 @@ def test_assemble_and_inject():
     assert torch.equal(x, ref)
     assert torch.equal(slotbuf[:, C:], ref.reshape(K * T, C).to(BF16)) and (slotbuf[:, :C] == 0).all()
     assert torch.equal(camout[:, C:], ref[:, 0])
+    # layers without a snapshot: only the camera-token rows are touched (one block per frame)
+    inj2 = randn(K, C, seed=7)
+    cam2 = torch.zeros(K, 2 * C, device="cuda")
+    ops.inject_snapshot(x, inj2, None, cam2, K, T, C, 0)
+    ref[:, 0] += inj2
+    assert torch.equal(x, ref) and torch.equal(cam2[:, :C], ref[:, 0]) and (cam2[:, C:] == 0).all()
 
 
 def test_depth_im2col_matches_reference_normalisation():
