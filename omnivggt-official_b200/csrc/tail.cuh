@@ -9,6 +9,14 @@
 // (kx, k-step) adds [W_ky=2 | W_ky=1 | W_ky=0] x row r into the three neighbouring blocks: the A row block (136 x 64 halves) is read
 // from shared memory once per kx instead of once per (ky, kx), which is what bounds the N = 32 formulation (5 KB of operand reads
 // per 16-clock MMA).  Blocks are zeroed by the epilogue warps when they drain them, so every MMA accumulates.
+//
+// Roles (512 threads, one CTA per SM, 222 KB of shared memory, all 512 TMEM columns):
+//   warp 0        loads the 72 KB of weights once (TMA), issues the MMAs, commits "A stage free" / "output row finished";
+//   warps 1-3, 8-15 (352 threads) producers: one thread bulk-copies the strip's source rows into a 4-row ring two rows ahead of use,
+//                 all of them blend vertically + horizontally (fp32, packed f32x2) and write the swizzled A stage (2 stages);
+//   warps 4-7     epilogue: TMEM block -> + bias + conv(position embedding) tables (the convolution is linear: its image under the
+//                 3x3 kernel separates into gx[row class][x] + gy[column class][y], tail_tables_kernel) -> ReLU -> 1x1 -> activations.
+// Work items: (frame, strip, segment of rows) with two halo rows per segment, about three per SM.
 #pragma once
 #include "ptx.cuh"
 
@@ -27,7 +35,7 @@ struct TailParams {
   float sy, sx;
   int outc, head_act, f16;
   int n_strips, n_segs, seg_rows, n_items;
-  long long* prof;      // debug: clock64 stamps of CTA 0's first 64 rows, 8 slots per row (nullptr: off)
+  long long* prof;      // debug: clock64 stamps of CTA 0's first 192 rows, 8 slots per row (nullptr: off)
 };
 #define OVG_FT_STAMP(cnt, slot)                                                                   \
   do {                                                                                            \
